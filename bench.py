@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- ray-steps/s of the RK3 + flux-deposition hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rays R]
+
+A "step" is one lprop.RK3 step (3 RK stages, 3 flux depositions, mean-flow update) over the
+synthetic column ensemble of BASELINE.json configs[1]: R = 1e6 ray volumes per GPU, constant N,
+zero mean wind.  One JSON line is printed by rank 0.
+
+  value     device-resident throughput: inputs already in HBM, per-step CUDA-event timing on the launch
+            stream, L2 flushed (256 MiB write) between timed steps, max over ranks.
+  e2e       the same step through the reference-facing call lprop.RK3(dt, var) with HOST (pinned) numpy
+            buffers: H2D of the step's inputs + kernels + D2H of rr, mm, uu, vv inside the timed region.
+  roofline  dominant kernel (pass B: 3 RK stages + 1 deposit + store) against the measured HBM peak.
+  cpu_baseline  the oracle port (C restatement of the reference, 1 thread) on this box's host cores.
+
+--impl reference times the reference's CPU algorithm (the oracle port; the reference itself is Python
+and cannot travel to the GPU box) with all host threads on the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "python-msgwam_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ray-steps/sec (RK step incl. flux deposition)"
+UNIT = "ray-steps/s"
+A_STEP = 96.0      # algorithmic B/ray-step, SURVEY.md 8(d): 10 fp64 fields read once + rr, mm written once
+A_PASS_A = 72.0    # pass A: 9 fields read (dens, ff, rr, drr, kk, ll, mm, dmm, dkk*dll), nothing written
+A_PASS_B = 88.0    # pass B: the same 9 fields read + rr, mm written
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scenario(n, rank):
+    from msgwam_b200 import scenarios
+    return scenarios.column_ensemble(n, seed=1234 + rank, ngrid=1001)
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference algorithm on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import oracle
+    n = args.rays if args.steps <= 30 else min(args.rays, 250_000)     # bounded sample per step
+    sc = make_scenario(n, 0)
+    best = None
+    tmax = oracle.max_threads()
+    for nthreads in sorted({1, tmax}, reverse=True):
+        orc = oracle.Oracle(sc.oracle_cfg(), nthreads=nthreads)
+        for _ in range(max(args.warmup, 1) if nthreads == tmax else 1):
+            orc.RK3(sc.dt, sc.var())
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.RK3(sc.dt, sc.var())
+        dt = time.perf_counter() - t0
+        rate = n * args.steps / dt
+        if best is None or rate > best[0]:
+            best = (rate, nthreads, dt)
+    rate, cores, dt = best
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 1e6 ray volumes, 1-D column, constant N, zero mean wind, G=1000", "rays": n,
+                   "grid_levels": 1000, "dt_s": sc.dt},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "oracle/msgwam_oracle.c (C restatement of lib/libprop.py RK3+rhs_default+wave_projection; the "
+                                   "Python reference cannot run on the GPU box and does ~2.3e4 ray-steps/s, BASELINE.md) on %d rays per step, "
+                                   "%d steps, best of {1,%d} OpenMP threads" % (n, args.steps, tmax)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import msgwam_b200.libprop as lprop
+    from msgwam_b200._engine import Engine
+    from msgwam_b200._cabi import check, lib
+    from msgwam_b200.ensemble import RayEnsemble
+
+    n = args.rays
+    sc = make_scenario(n, rank)
+    sc.install(lprop)
+    eng = Engine.get()
+    dev = eng.device
+    ens = RayEnsemble.from_scenario(sc)
+    p = ens.params(sc.dt)
+    g = eng.grid_struct(ens.grid_devs)
+    rays = ens._rays()
+    rr_out, mm_out = eng.empty(n), eng.empty(n)
+    uu_out, vv_out = eng.empty(ens.G), eng.empty(ens.G)
+    nc = ens.G - 1
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    P = eng.ptr
+
+    def reduce_(t):
+        if world > 1:
+            dist.all_reduce(t)
+
+    def pass_a():
+        check(lib.msgwam_column_pass_a(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), eng.stream), "pass_a")
+
+    def pass_b():
+        check(lib.msgwam_column_pass_b(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out), eng.stream), "pass_b")
+
+    def finish():
+        check(lib.msgwam_column_finish(p, g, P(ens.uu), P(ens.vv), P(ens.work), P(uu_out), P(vv_out), eng.stream), "finish")
+
+    def step():          # out of place: every timed step does identical work on the same input state
+        pass_a(); reduce_(ens.work[:4 * nc]); pass_b(); reduce_(ens.work[4 * nc:]); finish()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_(); step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- value: device-resident steps, per-step events, L2 flushed between steps ------------------
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()
+        a.record(); step(); b.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    t_steps = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    tt = torch.tensor([t_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_steps = float(tt.item())
+    launches = 3 * args.steps
+
+    # ---- per-kernel timing for the roofline (single rank's kernels; no collectives inside) --------
+    ka, kb, kf = [], [], []
+    for _ in range(max(3, min(args.steps, 20))):
+        flush.zero_()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(); pass_a(); e[1].record(); reduce_(ens.work[:4 * nc]); pass_b_start = torch.cuda.Event(enable_timing=True)
+        pass_b_start.record(); pass_b(); e[2].record(); reduce_(ens.work[4 * nc:]); fin0 = torch.cuda.Event(enable_timing=True)
+        fin0.record(); finish(); e[3].record()
+        torch.cuda.synchronize()
+        ka.append(e[0].elapsed_time(e[1])); kb.append(pass_b_start.elapsed_time(e[2])); kf.append(fin0.elapsed_time(e[3]))
+    t_a, t_b, t_f = (statistics.mean(x) * 1e-3 for x in (ka, kb, kf))
+
+    # ---- e2e: the reference-facing call with host buffers ------------------------------------------
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    keep = [pinned(np.ascontiguousarray(a)) for a in list(sc.state) + [sc.uu, sc.vv, sc.dkk, sc.dll, sc.rr_mm_area]]
+    var = np.empty(11, dtype=object)
+    for i in range(11):
+        var[i] = keep[i].numpy()
+    lprop.set_statics(dkk=keep[11].numpy(), dll=keep[12].numpy(), rr_mm_area=keep[13].numpy())
+    h2d = 10 * n * 8 + (ens.G + 1 + 6 * ens.G) * 8          # dens, phi, rr, drr, kk, ll, mm, dmm, dkk, dll + grid fields
+    d2h = 2 * n * 8 + 2 * ens.G * 8                          # rr, mm, uu, vv
+    if world == 1:
+        def e2e_step():
+            return lprop.RK3(sc.dt, var)
+    else:
+        from msgwam_b200.distributed import rk3_host_sharded
+        def e2e_step():
+            return rk3_host_sharded(lprop, sc.dt, var)
+    k_e2e = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        out = e2e_step()
+        _ = float(out[9][0])                                 # the step's result is read on the host
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        orc = oracle.Oracle(sc.oracle_cfg(), nthreads=1)
+        orc.RK3(sc.dt, sc.var())
+        t0 = time.perf_counter(); reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 40):
+            orc.RK3(sc.dt, sc.var()); reps += 1
+        dtc = time.perf_counter() - t0
+        cpu = {"value": n * reps / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "oracle port (C, 1 thread, -O2, no FMA) on the full %d-ray ensemble, %d RK3 steps in %.1f s; "
+                         "the unmodified Python reference does ~2.3e4 ray-steps/s on one core (BASELINE.md)" % (n, reps, dtc),
+               "host_cpus": os.cpu_count()}
+
+    peak, peak_src = measured_peaks()
+    total_rays = n * world
+    value = total_rays * args.steps / t_steps
+    ach_b = A_PASS_B * n / t_b / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_steps / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 1e6 ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000",
+                   "rays_per_gpu": n, "grid_levels": ens.G, "dt_s": sc.dt, "l2": "flushed between timed steps (256 MiB write)",
+                   "parallelism": "rays sharded, %d rank(s); all-reduce of the deposited flux twice per step" % world,
+                   "mode": "M1 coupled (reference RK3 semantics: mean flow inside the RK state), 2 ray sweeps per step"},
+        "roofline": {"bound": "hbm", "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak, "traffic": None,
+                     "kernel": "column_pass<1> (pass B: stages 1-3 + deposit + store)",
+                     "algorithmic_bytes_per_ray": A_PASS_B, "kernel_ms": t_b * 1e3, "peak_source": peak_src,
+                     "other_kernels": {"column_pass<0>": {"ms": t_a * 1e3, "achieved_gbs": A_PASS_A * n / t_a / 1e9,
+                                                          "algorithmic_bytes_per_ray": A_PASS_A},
+                                       "column_finish": {"ms": t_f * 1e3}},
+                     "step": {"algorithmic_bytes_per_ray_step": A_STEP,
+                              "achieved_gbs": A_STEP * total_rays * args.steps / t_steps / 1e9 / world,
+                              "frac": A_STEP * total_rays * args.steps / t_steps / 1e9 / world / peak}},
+        "e2e": {"value": total_rays * k_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": k_e2e, "api": "msgwam_b200.libprop.RK3(dt, var) with pinned numpy buffers"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "wall_s_timed_region_incl_flush": wall,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=1_000_000, help="ray volumes per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

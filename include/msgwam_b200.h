@@ -1,0 +1,203 @@
+/*
+ * msgwam_b200.h -- C ABI of the B200-native replacement for python-msgwam's hot path
+ * (Runge-Kutta stepping of the ray-volume equations + pseudo-momentum-flux deposition).
+ *
+ * The reference has no FFI: its "plugin API" is the Python module namespace of
+ * /root/reference/lib/libprop.py (imported as `lprop` at /root/reference/raytracer.py:2).
+ * Every entry point below names the reference callable(s) it replaces (L:nnn =
+ * lib/libprop.py line, R:nnn = raytracer.py line).  The ctypes binding a maintainer
+ * adds on the reference side is shown in INTEGRATION.md; the shipped binding is
+ * python-msgwam_b200/msgwam_b200/_cabi.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All floating point data is IEEE binary64.
+ *   - Pointers named d_* / inside msgwam_rays_t / msgwam_grid_t are DEVICE pointers owned by the
+ *     caller (torch tensors in the shipped host code); h_* are HOST pointers.
+ *   - No hidden allocations: scratch memory is passed in; its size comes from the *_bytes helpers.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Nothing synchronises
+ *     the stream unless stated.
+ *   - Return value: 0 = ok, > 0 = cudaError_t of the failing runtime call / launch,
+ *     < 0 = MSGWAM_E_* argument error.  msgwam_error_string() explains either.
+ *   - Scalars that the reference derives with Python-float arithmetic (bvf**2, 2*ROT_EARTH,
+ *     2*ROT_EARTH*sin(phi0), kappa**2*.5, np.diff(grid[:2])[0] ...) are derived by the host
+ *     binding with the same expressions and arrive in msgwam_params_t, so that no libm/pow
+ *     difference can enter (see _cabi.snapshot_params()).
+ */
+#ifndef MSGWAM_B200_H
+#define MSGWAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSGWAM_ABI_VERSION 1
+
+#define MSGWAM_E_BADARG      (-1)   /* null pointer / negative size / inconsistent arguments   */
+#define MSGWAM_E_GRID_SIZE   (-2)   /* G too small (< 3) or too large for the fused column kernels */
+#define MSGWAM_E_UNSUPPORTED (-3)   /* mode not handled by this entry point                     */
+
+/* model_config / module globals read on the hot path (SURVEY.md section 5, L:3-11, 380-383, 534, 582-584, 633) */
+typedef struct msgwam_params {
+    double dt;          /* time step passed to RK3 / rhs_default / saturation                     */
+    double n2;          /* model_config['bvf'] ** 2                                L:383           */
+    double two_rot;     /* 2 * ROT_EARTH                                           L:382           */
+    double rad_earth;   /* RAD_EARTH                                               L:3             */
+    double c8rot2;      /* 8 * ROT_EARTH**2                                        L:491           */
+    double f0;          /* 2 * ROT_EARTH * np.sin(model_config['phi0'])            L:535, 554, 589 */
+    double f0sq;        /* f0 ** 2                                                 L:597, 601      */
+    double k2half;      /* model_config['kappa']**2 * .5                           L:601           */
+    double dz_grid;     /* np.diff(grid[:2])[0]                                    L:349, 662      */
+    double dz_grids;    /* np.diff(grids[:2])[0]  (the deposit receives `grids`)   L:123, 657      */
+    double inv_dz_grid; /* 1.0 / dz_grid  (correctly rounded; used by exact-division-by-invariant)  */
+    double inv_dz_grids;/* 1.0 / dz_grids                                                           */
+    int32_t G;          /* len(grids) == len(grid) - 1                                              */
+    int32_t hprop;      /* HPROP_GLOBAL                                            L:5             */
+    int32_t saturate_online; /* model_config['saturate_online']                    L:633           */
+    int32_t reserved;
+} msgwam_params_t;
+
+/* Structure-of-arrays ray store: the 9 state slots of the reference's state vector
+ * (R:160-172, L:629), the per-ray statics (L:630-632) and two derived statics. */
+typedef struct msgwam_rays {
+    const double *dens, *lam, *phi, *rr, *drr, *kk, *ll, *mm, *dmm;
+    const double *dkk, *dll, *rr_mm_area;
+    const double *ff;    /* 2*ROT_EARTH*sin(phi)   (msgwam_derive_statics; column mode only) */
+    const double *pkl;   /* dkk*dll                (msgwam_derive_statics; column mode only) */
+} msgwam_rays_t;
+
+/* Background profiles on the 1-D mean-flow grid (L:6-9). */
+typedef struct msgwam_grid {
+    const double *grid;     /* (G+1,) cell edges                 lprop.grid              */
+    const double *grids;    /* (G,)   staggered grid             lprop.grids             */
+    const double *rhobar;   /* (G,)                              lprop.rhobar            */
+    const double *pg;       /* (2,G)                             lprop.pressure_gradient */
+} msgwam_grid_t;
+
+int         msgwam_abi_version(void);
+const char *msgwam_error_string(int code);
+/* number of SMs / max dynamic shared memory of device 0 as seen by the library (diagnostics) */
+int         msgwam_device_info(int *sm_count, int *max_smem_optin);
+
+/* ---- derived statics ------------------------------------------------------------------------
+ * ff = 2*ROT_EARTH*sin(phi) (L:382, 446) and pkl = dkk*dll (first product of L:137), once per
+ * upload; phi is constant while HPROP_GLOBAL is False, dkk/dll are statics. */
+int msgwam_derive_statics(const double *d_phi, const double *d_dkk, const double *d_dll,
+                          double *d_ff, double *d_pkl, int64_t n, double two_rot, void *stream);
+
+/* ---- fused column-mode RK3 step  (replaces RK3 L:680-700 with rhs = rhs_default L:618-676,
+ *      for HPROP_GLOBAL == False and saturate_online == False: only rr and mm change) --------
+ *
+ * The mean flow is part of the RK state, so stage s+1 needs the deposit of ALL rays at stage s:
+ *   pass A : deposit D(r0); stage 1 with u0; deposit D(r1)                      (reads 9 fields)
+ *   [multi-GPU: all-reduce D0|D1 here -- they are contiguous: 4*(G-1) doubles]
+ *   pass B : stage 1 (recomputed), stage 2 with u1, deposit D(r2), stage 3 with u2; write rr, mm
+ *   [multi-GPU: all-reduce D2: 2*(G-1) doubles]
+ *   finish : u3, v3 from u0, D0, D1, D2; zeroes the deposit buffers for the next step
+ * d_work: msgwam_column_work_doubles(G) doubles, zero-initialised by the caller once; layout
+ * D0 (2,G-1) | D1 (2,G-1) | D2 (2,G-1).  rr_out/mm_out may alias rays->rr / rays->mm.
+ */
+int64_t msgwam_column_work_doubles(int32_t G);
+int msgwam_column_pass_a(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                         const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                         double *d_work, void *stream);
+int msgwam_column_pass_b(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                         const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                         double *d_work, double *d_rr_out, double *d_mm_out, void *stream);
+int msgwam_column_finish(const msgwam_params_t *p, const msgwam_grid_t *grid,
+                         const double *d_uu, const double *d_vv, double *d_work,
+                         double *d_uu_out, double *d_vv_out, void *stream);
+/* single-GPU convenience: pass A, pass B, finish on `stream` */
+int msgwam_column_step(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                       const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                       double *d_work, double *d_rr_out, double *d_mm_out,
+                       double *d_uu_out, double *d_vv_out, void *stream);
+
+/* ---- general single-stage right-hand side  (replaces rhs_default L:618-676, every branch:
+ *      HPROP on/off, saturate_online on/off).  d_tend[9] receive the nine ray tendencies in
+ *      state-vector order, d_proj (2,G-1) the deposit of wave_projection(var=0) (must be zero
+ *      on entry), then msgwam_grid_tendency turns the deposit into du_st, dv_st (L:659-666). */
+int msgwam_rhs_rays(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                    const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                    double *const d_tend[9], double *d_proj, void *stream);
+int msgwam_grid_tendency(const msgwam_params_t *p, const msgwam_grid_t *grid,
+                         const double *d_uu, const double *d_vv, const double *d_proj,
+                         double *d_du, double *d_dv, void *stream);
+/* du_dt (which = 0, L:523-539: f0*wind - (pg + flux_gradient)/rhobar) and dv_dt (which = 1, L:542-558:
+ * -f0*wind - ...) from an already differentiated flux; d_pg is the matching row of pressure_gradient. */
+int msgwam_mean_flow_tendency(int32_t which, double f0, int32_t G, const double *d_wind,
+                              const double *d_flux_gradient, const double *d_rhobar, const double *d_pg,
+                              double *d_out, void *stream);
+/* low-storage RK update of one array (L:693-698): stage 0: q = dt*t, x_out = x + q/3;
+ * stage 1,2: q = dt*t - a*q, x_out = x + b*q. */
+int msgwam_rk_update(int32_t stage, double dt, const double *d_tend, double *d_q,
+                     const double *d_x, double *d_x_out, int64_t n, void *stream);
+
+/* ---- deposition  (replaces wave_projection L:92-221, var = 0..4, any uniform grid) ----------
+ * out sizes: var 0 -> 2*(ng-1); 1,2 -> ng-1; 3 -> ng; 4 -> 2*ng doubles, zeroed by the call.
+ * dz = np.diff(grid[:2])[0] of the grid passed (L:123) and inv_dz = 1.0/dz, derived by the host. */
+int msgwam_wave_projection(int32_t var, const msgwam_params_t *p, int64_t n,
+                           const double *d_dens, const double *d_phi,
+                           const double *d_rr_low, const double *d_rr_up,
+                           const double *d_kk, const double *d_ll,
+                           const double *d_mm_low, const double *d_mm_up,
+                           const double *d_dkk, const double *d_dll, const double *d_dmm,
+                           const double *d_grid, int32_t ng, double dz, double inv_dz,
+                           double *d_out, void *stream);
+
+/* ---- saturation  (replaces saturation L:561-615; direct = 0 tendency, 1 clamp) --------------*/
+int msgwam_saturation(const msgwam_params_t *p, int64_t n, int32_t direct,
+                      const double *d_dens, const double *d_rr, const double *d_rr_st,
+                      const double *d_drr, const double *d_drr_st,
+                      const double *d_kk, const double *d_ll,
+                      const double *d_mm, const double *d_mm_st,
+                      const double *d_dkk, const double *d_dll, const double *d_area,
+                      const double *d_grids, const double *d_rhobar, double *d_out, void *stream);
+
+/* ---- point functions (replace omega L:369, cg_rr L:434, cg_lambda L:386, cg_phi L:410,
+ *      dk_dt L:451, dl_dt L:474, dm_dt L:502, gradients L:328) ------------------------------
+ * op selects the function; unused inputs may be NULL.  For MSGWAM_OP_OMEGA_F the latitude is the
+ * scalar `f`/`f2` pair (2*ROT*sin(phi), its square) instead of d_phi.  gradients writes
+ * 4 arrays (uu_ray, vv_ray, du_dz_ray, dv_dz_ray) of n doubles into d_out. */
+enum {
+    MSGWAM_OP_OMEGA = 0, MSGWAM_OP_OMEGA_F = 1, MSGWAM_OP_CG_RR = 2, MSGWAM_OP_CG_LAMBDA = 3,
+    MSGWAM_OP_CG_PHI = 4, MSGWAM_OP_DK_DT = 5, MSGWAM_OP_DL_DT = 6, MSGWAM_OP_DM_DT = 7,
+    MSGWAM_OP_GRADIENTS = 8
+};
+int msgwam_pointwise(int32_t op, const msgwam_params_t *p, int64_t n,
+                     const double *d_kk, const double *d_ll, const double *d_mm,
+                     const double *d_phi, const double *d_rr, double f, double f2,
+                     const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                     double *d_out, void *stream);
+
+/* ---- stream compaction of the ray store (ray deletion; SURVEY.md 7.3-6, no reference code) --
+ * keep[i] != 0 keeps ray i.  nfields arrays are compacted stably from d_in[f] to d_out[f]
+ * (d_out[f] != d_in[f]).  d_count receives the number of survivors (device int64).
+ * d_scratch: msgwam_compact_scratch_bytes(n) bytes. */
+int64_t msgwam_compact_scratch_bytes(int64_t n);
+int msgwam_flag_rays(const msgwam_params_t *p, int64_t n, const double *d_rr, const double *d_drr,
+                     const double *d_mm, double m_crit, uint8_t *d_keep, void *stream);
+int msgwam_compact(int64_t n, const uint8_t *d_keep, int32_t nfields,
+                   const double *const d_in[], double *const d_out[], int64_t *d_count,
+                   void *d_scratch, void *stream);
+
+/* ---- host-buffer entry point: the call the reference-facing shim makes for numpy inputs -----
+ * Copies the step's inputs host->device, runs the column step, copies rr, mm, uu, vv back.
+ * All h_* are host pointers (pinned or pageable); d_stage is a device scratch of
+ * msgwam_host_stage_doubles(n, G) doubles; d_work as in msgwam_column_step.
+ * Synchronises `stream` before returning (the outputs are host memory). */
+int64_t msgwam_host_stage_doubles(int64_t n, int32_t G);
+int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n,
+                           const double *const h_state[9], const double *h_dkk, const double *h_dll,
+                           const double *h_uu, const double *h_vv,
+                           const double *h_grid, const double *h_grids, const double *h_rhobar,
+                           const double *h_pg,
+                           double *h_rr_out, double *h_mm_out, double *h_uu_out, double *h_vv_out,
+                           double *d_stage, double *d_work, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSGWAM_B200_H */

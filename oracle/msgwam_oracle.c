@@ -380,14 +380,22 @@ void orc_rk3(double dt, long n, double *const state[9], double *uu, double *vv,
         const double *cst[9];
         for (int f = 0; f < 9; ++f) cst[f] = state[f];
         orc_rhs_default(dt, n, cst, uu, vv, statics, grid, grids, rhobar, pg, P, tend, du, dv, NULL);
+        if (P->nthreads > 1) {
+            /* timing mode: one parallel sweep over the rays updates all nine fields (same arithmetic) */
+            const double as = a[stage], bs = b[stage];
+            #pragma omp parallel for schedule(static) num_threads(P->nthreads)
+            for (long i = 0; i < n; ++i)
+                for (int f = 0; f < 9; ++f) {
+                    if (stage == 0) { qq[f][i] = dt * tend[f][i]; state[f][i] = state[f][i] + qq[f][i] / 3; }
+                    else { qq[f][i] = dt * tend[f][i] - as * qq[f][i]; state[f][i] = state[f][i] + bs * qq[f][i]; }
+                }
+        } else
         for (int f = 0; f < 9; ++f) {
             double *x = state[f], *q = qq[f]; const double *t = tend[f];
             if (stage == 0) {
-                #pragma omp parallel for schedule(static) if (P->nthreads > 1) num_threads(P->nthreads > 1 ? P->nthreads : 1)
                 for (long i = 0; i < n; ++i) { q[i] = dt * t[i]; x[i] = x[i] + q[i] / 3; }     /* L:693-694 */
             } else {
                 const double as = a[stage], bs = b[stage];
-                #pragma omp parallel for schedule(static) if (P->nthreads > 1) num_threads(P->nthreads > 1 ? P->nthreads : 1)
                 for (long i = 0; i < n; ++i) { q[i] = dt * t[i] - as * q[i]; x[i] = x[i] + bs * q[i]; }   /* L:695-698 */
             }
         }

@@ -1,0 +1,519 @@
+// general.cu -- every branch of the reference right-hand side, one stage at a time, plus the
+// step-adjacent functions of the drop-in boundary (wave_projection var 0..4, saturation, the point
+// functions and the low-storage update).  These kernels serve
+//   * rhs_default called directly / plugged into RK3 by the user (L:618-676),
+//   * RK3 when HPROP_GLOBAL or saturate_online is on (all nine ray fields then change),
+//   * the diagnostics around the step (R:183-188, 213-231).
+// The BASELINE configurations run through column_step.cu; this file is the complete, slower path.
+#include "common.cuh"
+#include "deposit.cuh"
+
+namespace {
+
+using namespace mw;
+
+constexpr int NT = 256;
+
+// gradients() (L:349-358) without tables: du_dz/dv_dz on grid[1:-1] evaluated on the fly, which is
+// bit-identical to building the table first.
+__device__ __forceinline__ void shear_interp(double x, const double *__restrict__ grid, const double *__restrict__ uu,
+                                             const double *__restrict__ vv, int G, double dzg, double rdz,
+                                             double &du_ray, double &dv_ray)
+{
+    const int nc = G - 1;
+    const double *xg = grid + 1;
+    if (x != x) { du_ray = x; dv_ray = x; return; }
+    int j; bool flat;
+    if (x <= xg[0]) { j = 0; flat = true; }
+    else if (x >= xg[nc - 1]) { j = nc - 1; flat = true; }
+    else { j = interp_locate(x, xg, nc, rdz); flat = false; }
+    const double fu0 = dvd(sub(uu[j + 1], uu[j]), dzg), fv0 = dvd(sub(vv[j + 1], vv[j]), dzg);
+    const double dx = flat ? 0.0 : sub(x, xg[j]);
+    if (flat || dx == 0.0) { du_ray = fu0; dv_ray = fv0; return; }
+    const double fu1 = dvd(sub(uu[j + 2], uu[j + 1]), dzg), fv1 = dvd(sub(vv[j + 2], vv[j + 1]), dzg);
+    const double w = sub(xg[j + 1], xg[j]);
+    du_ray = add(mul(dvd(sub(fu1, fu0), w), dx), fu0);
+    dv_ray = add(mul(dvd(sub(fv1, fv0), w), dx), fv0);
+}
+
+struct RhsArgs {
+    msgwam_params_t p;
+    msgwam_rays_t r;
+    int64_t n;
+    const double *grid, *grids, *rhobar, *uu, *vv;
+    double *tend[9];
+};
+
+// saturation() core (L:582-604): returns max_dens_final and whether the clamp triggers
+__device__ __forceinline__ bool saturation_limit(const msgwam_params_t &p, double dt, double dens, double rr,
+                                                 double rr_st, double drr, double drr_st, double kk, double ll,
+                                                 double mm, double mm_st, double dkk, double dll, double area,
+                                                 const double *__restrict__ grids, const double *__restrict__ rhobar,
+                                                 double &maxd)
+{
+    const double rr_final = add(rr, mul(rr_st, dt));
+    const double drr_final = add(drr, mul(drr_st, dt));
+    const double mm_final = add(mm, mul(mm_st, dt));
+    const double dmm_final = dvd(area, drr_final);
+    const double rho = interp1(rr_final, grids, rhobar, p.G, p.inv_dz_grids);
+    const double kh2 = add(mul(kk, kk), mul(ll, ll));
+    const double omh = omega_from(kh2, mul(mm, mm), p.f0sq, p.n2);
+    const double psv = mul(mul(dkk, dll), dmm_final);
+    maxd = dvd(dvd(mul(mul(mul(p.k2half, rho), omh), p.n2), mul(mm_final, mm_final)), sub(mul(omh, omh), p.f0sq));
+    return maxd < mul(dens, psv);
+}
+
+// rhs_default's nine ray tendencies (L:629-651), all branches
+__global__ void __launch_bounds__(NT) rhs_rays_kernel(const RhsArgs a)
+{
+    const msgwam_params_t &p = a.p;
+    const int G = p.G;
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * NT) {
+        const double dens = a.r.dens[i], phi = a.r.phi[i], rr = a.r.rr[i], drr = a.r.drr[i];
+        const double kk = a.r.kk[i], ll = a.r.ll[i], mm = a.r.mm[i], dmm = a.r.dmm[i];
+        const double sphi = sin(phi), cphi = cos(phi);
+        const double ff = mul(p.two_rot, sphi), f2 = mul(ff, ff);
+        const double kh2 = add(mul(kk, kk), mul(ll, ll)), m2 = mul(mm, mm);
+        const double vk = add(kh2, m2);
+        const double om = omega_from(kh2, m2, f2, p.n2);
+        const double cgr = dvd(dvd(mul(-mm, sub(mul(om, om), f2)), om), vk);      // L:448
+        double du_ray, dv_ray;
+        shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
+        double cgl = 0.0, cgp = 0.0;
+        if (p.hprop) {                                                            // L:400-405, 424-429
+            const double uu_ray = interp1(rr, a.grids, a.uu, G, p.inv_dz_grids);
+            const double vv_ray = interp1(rr, a.grids, a.vv, G, p.inv_dz_grids);
+            const double nd = sub(p.n2, mul(om, om));
+            cgl = add(mul(dvd(dvd(kk, om), vk), nd), uu_ray);
+            cgp = add(mul(dvd(dvd(ll, om), vk), nd), vv_ray);
+        }
+        const double rad = add(p.rad_earth, rr);
+        const double drr_st = mul(.5, add(cgr, cgr));                             // L:640
+        const double ddrr_st = sub(cgr, cgr);                                     // L:641
+        double dkk_st = 0.0, dll_st = 0.0;
+        if (p.hprop) {
+            const double tphi = tan(phi);
+            const double zero = add(mul(kk, 0.0), mul(ll, 0.0));
+            const double g_lam = dvd(dvd(zero, rad), cphi);                       // L:465
+            dkk_st = sub(mul(dvd(kk, rad), sub(mul(tphi, cgp), cgr)), g_lam);     // L:468-469
+            const double g_phi = dvd(zero, rad);                                  // L:489
+            const double df2 = mul(mul(mul(p.c8rot2, sphi), cphi), 1.0);          // L:491
+            const double t3 = mul(dvd(dvd(dvd(m2, 2.0), om), vk), df2);
+            const double sum = add(add(mul(ll, cgr), mul(mul(kk, tphi), cgl)), t3);
+            dll_st = sub(dvd(-sum, rad), g_phi);                                  // L:494-497
+        }
+        const double g_rr = add(mul(kk, du_ray), mul(ll, dv_ray));                // L:517
+        const double dmm_st = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), g_rr);   // L:519-520
+        double maxd;
+        const bool hit = saturation_limit(p, p.dt, dens, rr, drr_st, drr, ddrr_st, kk, ll, mm, dmm_st,
+                                          a.r.dkk[i], a.r.dll[i], a.r.rr_mm_area[i], a.grids, a.rhobar, maxd);
+        const double st = hit ? dvd(sub(maxd, dens), p.dt) : 0.0;                 // L:612-615
+        a.tend[0][i] = mul(p.saturate_online ? 1.0 : 0.0, st);                    // L:647
+        a.tend[1][i] = dvd(dvd(cgl, rad), cphi);                                  // L:638
+        a.tend[2][i] = dvd(cgp, rad);                                             // L:639
+        a.tend[3][i] = drr_st;
+        a.tend[4][i] = ddrr_st;
+        a.tend[5][i] = dkk_st;
+        a.tend[6][i] = dll_st;
+        a.tend[7][i] = dmm_st;
+        a.tend[8][i] = mul(dvd(dmm, drr), ddrr_st);                               // L:645
+    }
+}
+
+// ---- wave_projection, var = 0, 1, 2 ----------------------------------------------------------
+struct ProjArgs {
+    msgwam_params_t p;
+    int var, centered, use_smem;
+    int64_t n;
+    // centered == 0: edges given (the reference signature); centered == 1: a,b = centre, extent
+    const double *dens, *phi, *ra, *rb, *kk, *ll, *ma, *mb, *dkk, *dll, *dmm;
+    const double *grid;
+    int ng;
+    double dz, rdz;
+    double *out;
+};
+
+__global__ void __launch_bounds__(NT) project_kernel(const ProjArgs a)
+{
+    extern __shared__ double sm[];
+    const int nc = a.ng - 1;
+    const int ncomp = a.var == 0 ? 2 : 1;
+    double *h0, *h1;
+    const double *g;
+    if (a.use_smem) {
+        double *gs = sm; h0 = sm + a.ng; h1 = h0 + nc;
+        for (int j = threadIdx.x; j < a.ng; j += NT) gs[j] = a.grid[j];
+        for (int j = threadIdx.x; j < 2 * nc; j += NT) h0[j] = 0.0;
+        __syncthreads();
+        g = gs;
+    } else {
+        // grids too large for shared memory: accumulate straight into the output.  The second
+        // component of single-component variants goes to a dummy slot that is never non-zero.
+        g = a.grid; h0 = a.out; h1 = a.out + (ncomp == 2 ? nc : 0);
+    }
+    Acc acc; acc.clear();
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (NT / 32);
+    const int64_t gw = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    const int64_t per = (((a.n + nwarps - 1) / nwarps) + 31) & ~(int64_t)31;
+    const int64_t begin = gw * per;
+    const int64_t end = (begin + per < a.n) ? begin + per : a.n;
+    for (int64_t base = begin; base < end; base += 32) {
+        const int64_t i = base + lane;
+        const bool live = i < end;
+        double rl = 0.0, ru = 0.0, psv = 0.0, v0 = 0.0, v1 = 0.0;
+        int nlow = 0, nup = 0;
+        bool ok = false;
+        if (live) {
+            double ml, mu;
+            if (a.centered) {
+                const double hd = mul(.5, a.rb[i]), hm = mul(.5, a.mb[i]);
+                rl = sub(a.ra[i], hd); ru = add(a.ra[i], hd);
+                ml = sub(a.ma[i], hm); mu = add(a.ma[i], hm);
+            } else { rl = a.ra[i]; ru = a.rb[i]; ml = a.ma[i]; mu = a.mb[i]; }
+            ok = cell_range(rl, ru, a.dz, a.rdz, a.ng - 2, nlow, nup);
+            if (ok) {
+                psv = fabs(mul(mul(a.dkk[i], a.dll[i]), a.dmm[i]));              // L:137
+                const double dens = a.dens[i];
+                if (a.var == 2) v0 = dens;                                       // L:184
+                else {
+                    const double kk = a.kk[i], ll = a.ll[i];
+                    const double ff = mul(a.p.two_rot, sin(a.phi[i]));
+                    const double cgr = cg_rr_from(add(mul(kk, kk), mul(ll, ll)), mul(.5, add(ml, mu)), mul(ff, ff), a.p.n2);
+                    if (a.var == 0) { v0 = mul(mul(cgr, kk), dens); v1 = mul(mul(cgr, ll), dens); }   // L:148-149
+                    else v0 = mul(cgr, dens);                                    // L:167
+                }
+            }
+        }
+        deposit_cells(ok, nlow, nup, rl, ru, psv, v0, v1, a.dz, a.rdz, g, acc, h0, h1);
+    }
+    flush_acc(acc, h0, h1);
+    if (a.use_smem) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < ncomp * nc; j += NT) {
+            const double v = h0[j];
+            if (v != 0.0) atomicAdd(a.out + j, v);
+        }
+    }
+}
+
+// var = 3, 4: fluxes through the interfaces strictly inside the ray volume's cell range (L:199-219)
+__global__ void __launch_bounds__(NT) project_iface_kernel(const ProjArgs a)
+{
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * NT) {
+        int nlow, nup;
+        if (!cell_range(a.ra[i], a.rb[i], a.dz, a.rdz, a.ng - 2, nlow, nup)) continue;
+        const double psv = fabs(mul(mul(a.dkk[i], a.dll[i]), a.dmm[i]));
+        const double kk = a.kk[i], ll = a.ll[i], dens = a.dens[i];
+        const double ff = mul(a.p.two_rot, sin(a.phi[i]));
+        const double cgr = cg_rr_from(add(mul(kk, kk), mul(ll, ll)), mul(.5, add(a.ma[i], a.mb[i])), mul(ff, ff), a.p.n2);
+        const int b0 = max(nlow + 1, 1), b1 = min(nup - 1, a.ng - 2);
+        if (a.var == 3) {
+            const double t = mul(mul(cgr, dens), psv);
+            for (int nb = b0; nb <= b1; ++nb) atomicAdd(a.out + nb, t);
+        } else {
+            const double t0 = mul(mul(mul(cgr, kk), dens), psv), t1 = mul(mul(mul(cgr, ll), dens), psv);
+            for (int nb = b0; nb <= b1; ++nb) { atomicAdd(a.out + nb, t0); atomicAdd(a.out + a.ng + nb, t1); }
+        }
+    }
+}
+
+// ---- du_dt, dv_dt from the deposit (L:653-666, 523-558) -------------------------------------
+__global__ void grid_tendency_kernel(msgwam_params_t p, const double *__restrict__ rhobar, const double *__restrict__ pg,
+                                     const double *__restrict__ uu, const double *__restrict__ vv,
+                                     const double *__restrict__ D, double *__restrict__ du, double *__restrict__ dv)
+{
+    const int G = p.G, nc = G - 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < G; j += gridDim.x * blockDim.x) {
+        const int i0 = min(max(j - 1, 0), nc - 1), i1 = min(j, nc - 1);
+        const double g0 = dvd(sub(D[i1], D[i0]), p.dz_grid);
+        const double g1 = dvd(sub(D[nc + i1], D[nc + i0]), p.dz_grid);
+        const double rinv = dvd(1.0, rhobar[j]);
+        du[j] = sub(mul(p.f0, vv[j]), mul(rinv, add(pg[j], g0)));
+        dv[j] = sub(mul(-p.f0, uu[j]), mul(rinv, add(pg[G + j], g1)));
+    }
+}
+
+__global__ void mean_flow_tendency_kernel(int which, double f0, int G, const double *__restrict__ wind,
+                                          const double *__restrict__ fg, const double *__restrict__ rhobar,
+                                          const double *__restrict__ pg, double *__restrict__ out)
+{
+    const double f = which == 0 ? f0 : -f0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < G; j += gridDim.x * blockDim.x)
+        out[j] = sub(mul(f, wind[j]), mul(dvd(1.0, rhobar[j]), add(pg[j], fg[j])));
+}
+
+// ---- low-storage RK update (L:693-698) -------------------------------------------------------
+__global__ void rk_update_kernel(int stage, double dt, const double *__restrict__ t, double *__restrict__ q,
+                                 const double *x, double *xo, int64_t n)
+{
+    const double as = stage == 1 ? 5 / 9. : 153 / 128., bs = stage == 1 ? 15 / 16. : 8 / 15.;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (stage == 0) {
+            const double qq = mul(dt, t[i]);
+            q[i] = qq; xo[i] = add(x[i], dvd(qq, 3.0));
+        } else {
+            const double qq = sub(mul(dt, t[i]), mul(as, q[i]));
+            q[i] = qq; xo[i] = add(x[i], mul(bs, qq));
+        }
+    }
+}
+
+// ---- saturation (L:561-615) ---------------------------------------------------------------------
+struct SatArgs {
+    msgwam_params_t p;
+    int64_t n; int direct;
+    const double *dens, *rr, *rr_st, *drr, *drr_st, *kk, *ll, *mm, *mm_st, *dkk, *dll, *area, *grids, *rhobar;
+    double *out;
+};
+
+__global__ void __launch_bounds__(NT) saturation_kernel(const SatArgs a)
+{
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * NT) {
+        double maxd;
+        const double dens = a.dens[i];
+        const bool hit = saturation_limit(a.p, a.p.dt, dens, a.rr[i], a.rr_st[i], a.drr[i], a.drr_st[i], a.kk[i], a.ll[i],
+                                          a.mm[i], a.mm_st[i], a.dkk[i], a.dll[i], a.area[i], a.grids, a.rhobar, maxd);
+        if (a.direct) a.out[i] = hit ? maxd : dens;                               // L:606-610
+        else a.out[i] = hit ? dvd(sub(maxd, dens), a.p.dt) : 0.0;                 // L:612-615
+    }
+}
+
+// ---- point functions ----------------------------------------------------------------------------
+struct PwArgs {
+    msgwam_params_t p;
+    int op; int64_t n;
+    const double *kk, *ll, *mm, *phi, *rr, *grid, *grids, *uu, *vv;
+    double f, f2;
+    double *out;
+};
+
+__global__ void __launch_bounds__(NT) pointwise_kernel(const PwArgs a)
+{
+    const msgwam_params_t &p = a.p;
+    const int G = p.G;
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * NT) {
+        if (a.op == MSGWAM_OP_GRADIENTS) {
+            const double rr = a.rr[i];
+            double du_ray, dv_ray;
+            shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
+            a.out[i] = interp1(rr, a.grids, a.uu, G, p.inv_dz_grids);             // L:357
+            a.out[a.n + i] = interp1(rr, a.grids, a.vv, G, p.inv_dz_grids);       // L:358
+            a.out[2 * a.n + i] = du_ray;                                          // L:355
+            a.out[3 * a.n + i] = dv_ray;                                          // L:356
+            continue;
+        }
+        const double kk = a.kk[i], ll = a.ll[i], mm = a.mm[i];
+        const double kh2 = add(mul(kk, kk), mul(ll, ll)), m2 = mul(mm, mm), vk = add(kh2, m2);
+        double sphi = 0.0, cphi = 1.0, f2;
+        if (a.op == MSGWAM_OP_OMEGA_F) f2 = a.f2;
+        else {
+            const double phi = a.phi[i];
+            sphi = sin(phi); cphi = cos(phi);
+            const double ff = mul(p.two_rot, sphi);
+            f2 = mul(ff, ff);
+        }
+        const double om = omega_from(kh2, m2, f2, p.n2);
+        if (a.op == MSGWAM_OP_OMEGA || a.op == MSGWAM_OP_OMEGA_F) { a.out[i] = om; continue; }
+        const double cgr = dvd(dvd(mul(-mm, sub(mul(om, om), f2)), om), vk);
+        if (a.op == MSGWAM_OP_CG_RR) { a.out[i] = cgr; continue; }
+        const double rr = a.rr[i];
+        double cgl = 0.0, cgp = 0.0;
+        if (p.hprop) {
+            const double nd = sub(p.n2, mul(om, om));
+            cgl = add(mul(dvd(dvd(kk, om), vk), nd), interp1(rr, a.grids, a.uu, G, p.inv_dz_grids));
+            cgp = add(mul(dvd(dvd(ll, om), vk), nd), interp1(rr, a.grids, a.vv, G, p.inv_dz_grids));
+        }
+        if (a.op == MSGWAM_OP_CG_LAMBDA) { a.out[i] = cgl; continue; }
+        if (a.op == MSGWAM_OP_CG_PHI) { a.out[i] = cgp; continue; }
+        const double rad = add(p.rad_earth, rr);
+        if (a.op == MSGWAM_OP_DM_DT) {
+            double du_ray, dv_ray;
+            shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
+            a.out[i] = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), add(mul(kk, du_ray), mul(ll, dv_ray)));
+            continue;
+        }
+        if (!p.hprop) { a.out[i] = 0.0; continue; }                               // L:470-471, 498-499
+        const double tphi = tan(a.phi[i]);
+        const double zero = add(mul(kk, 0.0), mul(ll, 0.0));
+        if (a.op == MSGWAM_OP_DK_DT) {
+            a.out[i] = sub(mul(dvd(kk, rad), sub(mul(tphi, cgp), cgr)), dvd(dvd(zero, rad), cphi));
+        } else {   // DL_DT
+            const double df2 = mul(mul(mul(p.c8rot2, sphi), cphi), 1.0);
+            const double t3 = mul(dvd(dvd(dvd(m2, 2.0), om), vk), df2);
+            const double sum = add(add(mul(ll, cgr), mul(mul(kk, tphi), cgl)), t3);
+            a.out[i] = sub(dvd(-sum, rad), dvd(zero, rad));
+        }
+    }
+}
+
+int g_sms = 0, g_smem = 0;
+int props()
+{
+    if (g_sms == 0) {
+        int rc = msgwam_device_info(&g_sms, &g_smem);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+inline int grid_for(int64_t n, int threads, int per_sm)
+{
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)g_sms * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int msgwam_rhs_rays(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n, const msgwam_grid_t *grid,
+                    const double *d_uu, const double *d_vv, double *const d_tend[9], double *d_proj, void *stream)
+{
+    if (!p || !rays || !grid || !d_uu || !d_vv || !d_tend || !d_proj || n < 0) return MSGWAM_E_BADARG;
+    if (p->G < 3) return MSGWAM_E_GRID_SIZE;
+    int rc = props();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n > 0) {
+        RhsArgs a{};
+        a.p = *p; a.r = *rays; a.n = n;
+        a.grid = grid->grid; a.grids = grid->grids; a.rhobar = grid->rhobar; a.uu = d_uu; a.vv = d_vv;
+        for (int f = 0; f < 9; ++f) { if (!d_tend[f]) return MSGWAM_E_BADARG; a.tend[f] = d_tend[f]; }
+        rhs_rays_kernel<<<grid_for(n, NT, 8), NT, 0, s>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    // wave_projection(dens, lam, phi, rr -/+ .5*drr, kk, ll, mm -/+ .5*dmm, dkk, dll, dmm, grids)  L:654-658
+    ProjArgs q{};
+    q.p = *p; q.var = 0; q.centered = 1; q.n = n;
+    q.dens = rays->dens; q.phi = rays->phi; q.ra = rays->rr; q.rb = rays->drr; q.kk = rays->kk; q.ll = rays->ll;
+    q.ma = rays->mm; q.mb = rays->dmm; q.dkk = rays->dkk; q.dll = rays->dll; q.dmm = rays->dmm;
+    q.grid = grid->grids; q.ng = p->G; q.dz = p->dz_grids; q.rdz = p->inv_dz_grids; q.out = d_proj;
+    if (n > 0) {
+        const size_t bytes = (size_t)(q.ng + 2 * (q.ng - 1)) * sizeof(double);
+        q.use_smem = bytes <= (size_t)g_smem;
+        if (q.use_smem) {
+            cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        project_kernel<<<grid_for(n, NT * 4, 4), NT, q.use_smem ? bytes : 0, s>>>(q);
+        return (int)cudaGetLastError();
+    }
+    return 0;
+}
+
+int msgwam_grid_tendency(const msgwam_params_t *p, const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                         const double *d_proj, double *d_du, double *d_dv, void *stream)
+{
+    if (!p || !grid || !d_uu || !d_vv || !d_proj || !d_du || !d_dv) return MSGWAM_E_BADARG;
+    if (p->G < 3) return MSGWAM_E_GRID_SIZE;
+    grid_tendency_kernel<<<(p->G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p, grid->rhobar, grid->pg, d_uu, d_vv,
+                                                                               d_proj, d_du, d_dv);
+    return (int)cudaGetLastError();
+}
+
+int msgwam_mean_flow_tendency(int32_t which, double f0, int32_t G, const double *d_wind, const double *d_flux_gradient,
+                              const double *d_rhobar, const double *d_pg, double *d_out, void *stream)
+{
+    if (which < 0 || which > 1 || G < 0) return MSGWAM_E_BADARG;
+    if (G == 0) return 0;
+    if (!d_wind || !d_flux_gradient || !d_rhobar || !d_pg || !d_out) return MSGWAM_E_BADARG;
+    mean_flow_tendency_kernel<<<(G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(which, f0, G, d_wind, d_flux_gradient,
+                                                                                 d_rhobar, d_pg, d_out);
+    return (int)cudaGetLastError();
+}
+
+int msgwam_rk_update(int32_t stage, double dt, const double *d_tend, double *d_q, const double *d_x, double *d_x_out,
+                     int64_t n, void *stream)
+{
+    if (stage < 0 || stage > 2 || n < 0 || (n > 0 && (!d_tend || !d_q || !d_x || !d_x_out))) return MSGWAM_E_BADARG;
+    if (n == 0) return 0;
+    int rc = props();
+    if (rc) return rc;
+    rk_update_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(stage, dt, d_tend, d_q, d_x, d_x_out, n);
+    return (int)cudaGetLastError();
+}
+
+int msgwam_wave_projection(int32_t var, const msgwam_params_t *p, int64_t n, const double *d_dens, const double *d_phi,
+                           const double *d_rr_low, const double *d_rr_up, const double *d_kk, const double *d_ll,
+                           const double *d_mm_low, const double *d_mm_up, const double *d_dkk, const double *d_dll,
+                           const double *d_dmm, const double *d_grid, int32_t ng, double dz, double inv_dz, double *d_out,
+                           void *stream)
+{
+    if (!p || var < 0 || var > 4 || n < 0 || ng < 3 || !d_grid || !d_out) return MSGWAM_E_BADARG;
+    if (n > 0 && (!d_dens || !d_phi || !d_rr_low || !d_rr_up || !d_kk || !d_ll || !d_mm_low || !d_mm_up || !d_dkk ||
+                  !d_dll || !d_dmm))
+        return MSGWAM_E_BADARG;
+    int rc = props();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t outlen = var == 0 ? 2 * (size_t)(ng - 1) : var == 4 ? 2 * (size_t)ng : var == 3 ? (size_t)ng : (size_t)(ng - 1);
+    cudaError_t e = cudaMemsetAsync(d_out, 0, outlen * sizeof(double), s);
+    if (e != cudaSuccess) return (int)e;
+    if (n == 0) return 0;
+    ProjArgs q{};
+    q.p = *p; q.var = var; q.centered = 0; q.n = n;
+    q.dens = d_dens; q.phi = d_phi; q.ra = d_rr_low; q.rb = d_rr_up; q.kk = d_kk; q.ll = d_ll;
+    q.ma = d_mm_low; q.mb = d_mm_up; q.dkk = d_dkk; q.dll = d_dll; q.dmm = d_dmm;
+    q.grid = d_grid; q.ng = ng; q.out = d_out;
+    q.dz = dz; q.rdz = inv_dz;
+    if (var >= 3) {
+        project_iface_kernel<<<grid_for(n, NT, 8), NT, 0, s>>>(q);
+        return (int)cudaGetLastError();
+    }
+    const size_t bytes = (size_t)(ng + 2 * (ng - 1)) * sizeof(double);
+    q.use_smem = bytes <= (size_t)g_smem;
+    if (q.use_smem) {
+        e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    project_kernel<<<grid_for(n, NT * 4, 4), NT, q.use_smem ? bytes : 0, s>>>(q);
+    return (int)cudaGetLastError();
+}
+
+int msgwam_saturation(const msgwam_params_t *p, int64_t n, int32_t direct, const double *d_dens, const double *d_rr,
+                      const double *d_rr_st, const double *d_drr, const double *d_drr_st, const double *d_kk,
+                      const double *d_ll, const double *d_mm, const double *d_mm_st, const double *d_dkk,
+                      const double *d_dll, const double *d_area, const double *d_grids, const double *d_rhobar,
+                      double *d_out, void *stream)
+{
+    if (!p || n < 0) return MSGWAM_E_BADARG;
+    if (n == 0) return 0;
+    if (!d_dens || !d_rr || !d_rr_st || !d_drr || !d_drr_st || !d_kk || !d_ll || !d_mm || !d_mm_st || !d_dkk || !d_dll ||
+        !d_area || !d_grids || !d_rhobar || !d_out)
+        return MSGWAM_E_BADARG;
+    int rc = props();
+    if (rc) return rc;
+    SatArgs a{*p, n, direct, d_dens, d_rr, d_rr_st, d_drr, d_drr_st, d_kk, d_ll, d_mm, d_mm_st, d_dkk, d_dll, d_area,
+              d_grids, d_rhobar, d_out};
+    saturation_kernel<<<grid_for(n, NT, 8), NT, 0, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int msgwam_pointwise(int32_t op, const msgwam_params_t *p, int64_t n, const double *d_kk, const double *d_ll,
+                     const double *d_mm, const double *d_phi, const double *d_rr, double f, double f2,
+                     const msgwam_grid_t *grid, const double *d_uu, const double *d_vv, double *d_out, void *stream)
+{
+    if (!p || op < 0 || op > MSGWAM_OP_GRADIENTS || n < 0) return MSGWAM_E_BADARG;
+    if (n == 0) return 0;
+    if (!d_out) return MSGWAM_E_BADARG;
+    const bool needs_wave = op != MSGWAM_OP_GRADIENTS;
+    const bool needs_phi = needs_wave && op != MSGWAM_OP_OMEGA_F;
+    const bool needs_pos = op >= MSGWAM_OP_CG_LAMBDA;
+    if ((needs_wave && (!d_kk || !d_ll || !d_mm)) || (needs_phi && !d_phi)) return MSGWAM_E_BADARG;
+    if (needs_pos && (!d_rr || !grid || !grid->grid || !grid->grids || !d_uu || !d_vv || p->G < 3)) return MSGWAM_E_BADARG;
+    int rc = props();
+    if (rc) return rc;
+    PwArgs a{};
+    a.p = *p; a.op = op; a.n = n; a.kk = d_kk; a.ll = d_ll; a.mm = d_mm; a.phi = d_phi; a.rr = d_rr;
+    if (grid) { a.grid = grid->grid; a.grids = grid->grids; }
+    a.uu = d_uu; a.vv = d_vv; a.f = f; a.f2 = f2; a.out = d_out;
+    pointwise_kernel<<<grid_for(n, NT, 8), NT, 0, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

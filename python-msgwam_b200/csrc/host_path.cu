@@ -1,0 +1,91 @@
+// host_path.cu -- the host-buffer entry point and the ABI bookkeeping.
+//
+// msgwam_rk3_column_host is what the reference-facing shim calls when the caller hands numpy arrays
+// to RK3 (R:160-175): every input of the step is copied host->device, the fused column step runs,
+// and the changed slots (rr, mm, uu, vv) are copied back.  lam, phi, dens, drr, kk, ll, dmm keep their
+// values in column mode (their tendencies are exactly zero, L:638-645 with HPROP off), so the shim
+// returns copies of the inputs for those slots and they are never moved over PCIe.
+#include "common.cuh"
+
+extern "C" {
+
+int msgwam_abi_version(void) { return MSGWAM_ABI_VERSION; }
+
+const char *msgwam_error_string(int code)
+{
+    switch (code) {
+    case 0: return "ok";
+    case MSGWAM_E_BADARG: return "msgwam: bad argument (null pointer, negative size or inconsistent sizes)";
+    case MSGWAM_E_GRID_SIZE: return "msgwam: grid size unsupported (G < 3, or shear tables exceed shared memory)";
+    case MSGWAM_E_UNSUPPORTED: return "msgwam: mode not supported by this entry point (column kernels need HPROP off and saturate_online off)";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "msgwam: unknown error";
+    }
+}
+
+static inline int64_t pad32(int64_t n) { return (n + 31) & ~(int64_t)31; }
+
+int64_t msgwam_host_stage_doubles(int64_t n, int32_t G)
+{
+    if (n < 0 || G < 3) return 0;
+    // 10 uploaded ray fields + ff + pkl + rr_out + mm_out, then grid (G+1), grids, rhobar, pg (2G), uu, vv, uu_out, vv_out
+    return 14 * pad32(n) + pad32(G + 1) + 8 * pad32(G);
+}
+
+int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *const h_state[9], const double *h_dkk,
+                           const double *h_dll, const double *h_uu, const double *h_vv, const double *h_grid,
+                           const double *h_grids, const double *h_rhobar, const double *h_pg, double *h_rr_out,
+                           double *h_mm_out, double *h_uu_out, double *h_vv_out, double *d_stage, double *d_work,
+                           void *stream)
+{
+    if (!p || n < 0 || !h_state || !h_uu || !h_vv || !h_grid || !h_grids || !h_rhobar || !h_pg || !h_uu_out || !h_vv_out ||
+        !d_stage || !d_work)
+        return MSGWAM_E_BADARG;
+    if (p->G < 3) return MSGWAM_E_GRID_SIZE;
+    if (n > 0 && (!h_dkk || !h_dll || !h_rr_out || !h_mm_out)) return MSGWAM_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t np = pad32(n), G = p->G, gp = pad32(G);
+    double *d = d_stage;
+    // state order: dens, lam, phi, rr, drr, kk, ll, mm, dmm  (lam is not needed on the device)
+    double *d_dens = d, *d_phi = d + np, *d_rr = d + 2 * np, *d_drr = d + 3 * np, *d_kk = d + 4 * np, *d_ll = d + 5 * np,
+           *d_mm = d + 6 * np, *d_dmm = d + 7 * np, *d_dkk = d + 8 * np, *d_dll = d + 9 * np, *d_ff = d + 10 * np,
+           *d_pkl = d + 11 * np, *d_rro = d + 12 * np, *d_mmo = d + 13 * np;
+    double *g = d + 14 * np;
+    double *d_grid = g, *d_grids = g + pad32(G + 1), *d_rho = d_grids + gp, *d_pg = d_rho + gp, *d_uu = d_pg + 2 * gp,
+           *d_vv = d_uu + gp, *d_uuo = d_vv + gp, *d_vvo = d_uuo + gp;
+    cudaError_t e;
+#define MW_H2D(dst, src, cnt)                                                                          \
+    do {                                                                                               \
+        if ((cnt) > 0) {                                                                               \
+            if (!(src)) return MSGWAM_E_BADARG;                                                        \
+            e = cudaMemcpyAsync((dst), (src), (size_t)(cnt) * sizeof(double), cudaMemcpyHostToDevice, s); \
+            if (e != cudaSuccess) return (int)e;                                                       \
+        }                                                                                              \
+    } while (0)
+    MW_H2D(d_grid, h_grid, G + 1); MW_H2D(d_grids, h_grids, G); MW_H2D(d_rho, h_rhobar, G); MW_H2D(d_pg, h_pg, 2 * G);
+    MW_H2D(d_uu, h_uu, G); MW_H2D(d_vv, h_vv, G);
+    MW_H2D(d_phi, h_state[2], n); MW_H2D(d_dkk, h_dkk, n); MW_H2D(d_dll, h_dll, n);
+    int rc = msgwam_derive_statics(d_phi, d_dkk, d_dll, d_ff, d_pkl, n, p->two_rot, stream);
+    if (rc) return rc;
+    MW_H2D(d_dens, h_state[0], n); MW_H2D(d_rr, h_state[3], n); MW_H2D(d_drr, h_state[4], n); MW_H2D(d_kk, h_state[5], n);
+    MW_H2D(d_ll, h_state[6], n); MW_H2D(d_mm, h_state[7], n); MW_H2D(d_dmm, h_state[8], n);
+#undef MW_H2D
+    msgwam_rays_t r{};
+    r.dens = d_dens; r.phi = d_phi; r.rr = d_rr; r.drr = d_drr; r.kk = d_kk; r.ll = d_ll; r.mm = d_mm; r.dmm = d_dmm;
+    r.dkk = d_dkk; r.dll = d_dll; r.ff = d_ff; r.pkl = d_pkl;
+    msgwam_grid_t gr{d_grid, d_grids, d_rho, d_pg};
+    rc = msgwam_column_step(p, &r, n, &gr, d_uu, d_vv, d_work, d_rro, d_mmo, d_uuo, d_vvo, stream);
+    if (rc) return rc;
+    if (n > 0) {
+        e = cudaMemcpyAsync(h_rr_out, d_rro, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpyAsync(h_mm_out, d_mmo, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = cudaMemcpyAsync(h_uu_out, d_uuo, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyAsync(h_vv_out, d_vvo, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize(s);
+}
+
+}  // extern "C"

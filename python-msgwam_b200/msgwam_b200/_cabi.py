@@ -1,0 +1,131 @@
+"""ctypes binding of libmsgwam_b200.so (include/msgwam_b200.h).
+
+There is no fallback: if the CUDA library is missing the import fails loudly, and every
+call raises on a non-zero status.  All scalars that the reference derives with Python-float
+arithmetic are derived here with the same expressions (``snapshot_params``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmsgwam_b200.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_void_p = ctypes.c_void_p
+
+
+class Params(ctypes.Structure):
+    _fields_ = [
+        ("dt", ctypes.c_double), ("n2", ctypes.c_double), ("two_rot", ctypes.c_double),
+        ("rad_earth", ctypes.c_double), ("c8rot2", ctypes.c_double), ("f0", ctypes.c_double),
+        ("f0sq", ctypes.c_double), ("k2half", ctypes.c_double), ("dz_grid", ctypes.c_double),
+        ("dz_grids", ctypes.c_double), ("inv_dz_grid", ctypes.c_double), ("inv_dz_grids", ctypes.c_double),
+        ("G", ctypes.c_int32), ("hprop", ctypes.c_int32), ("saturate_online", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+_RAY_FIELDS = ("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm", "dkk", "dll", "rr_mm_area", "ff", "pkl")
+
+
+class Rays(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in _RAY_FIELDS]
+
+
+class Grid(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in ("grid", "grids", "rhobar", "pg")]
+
+
+OP_OMEGA, OP_OMEGA_F, OP_CG_RR, OP_CG_LAMBDA, OP_CG_PHI, OP_DK_DT, OP_DL_DT, OP_DM_DT, OP_GRADIENTS = range(9)
+
+# every symbol include/msgwam_b200.h declares: name -> (restype, argtypes)
+_i64, _i32, _dbl, _vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, c_void_p
+_PP, _RP, _GP = ctypes.POINTER(Params), ctypes.POINTER(Rays), ctypes.POINTER(Grid)
+SIGNATURES = {
+    "msgwam_abi_version": (ctypes.c_int, []),
+    "msgwam_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "msgwam_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "msgwam_derive_statics": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _dbl, _vp]),
+    "msgwam_column_work_doubles": (_i64, [_i32]),
+    "msgwam_column_pass_a": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp]),
+    "msgwam_column_pass_b": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "msgwam_column_finish": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "msgwam_column_step": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "msgwam_rhs_rays": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp]),
+    "msgwam_grid_tendency": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "msgwam_mean_flow_tendency": (ctypes.c_int, [_i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "msgwam_rk_update": (ctypes.c_int, [_i32, _dbl, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "msgwam_wave_projection": (ctypes.c_int, [_i32, _PP, _i64] + [_vp] * 12 + [_i32, _dbl, _dbl, _vp, _vp]),
+    "msgwam_saturation": (ctypes.c_int, [_PP, _i64, _i32] + [_vp] * 15 + [_vp]),
+    "msgwam_pointwise": (ctypes.c_int, [_i32, _PP, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _GP, _vp, _vp, _vp, _vp]),
+    "msgwam_compact_scratch_bytes": (_i64, [_i64]),
+    "msgwam_flag_rays": (ctypes.c_int, [_PP, _i64, _vp, _vp, _vp, _dbl, _vp, _vp]),
+    "msgwam_compact": (ctypes.c_int, [_i64, _vp, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _vp]),
+    "msgwam_host_stage_doubles": (_i64, [_i64, _i32]),
+    "msgwam_rk3_column_host": (ctypes.c_int, [_PP, _i64, ctypes.POINTER(_vp)] + [_vp] * 14 + [_vp]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "msgwam_b200: %s is missing.  Build it with python-msgwam_b200/build.sh "
+            "(or __graft_entry__.build()); there is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.msgwam_abi_version() != 1:
+        raise ImportError("msgwam_b200: ABI version mismatch in %s" % LIB_PATH)
+    return lib
+
+
+lib = _load()
+
+
+class MsgwamError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.msgwam_error_string(int(rc)).decode()
+        raise MsgwamError("%s failed (%d): %s" % (what or "msgwam call", rc, msg))
+
+
+ROT_EARTH_DEFAULT = 7.2921e-5
+RAD_EARTH_DEFAULT = 6378e3
+
+
+def snapshot_params(dt, *, bvf, phi0, kappa, saturate_online, hprop, grid, grids,
+                    rot_earth=ROT_EARTH_DEFAULT, rad_earth=RAD_EARTH_DEFAULT) -> Params:
+    """POD snapshot of the module globals / model_config the hot path reads.
+
+    ``grid`` / ``grids`` are host arrays (or anything indexable whose first two entries can be read
+    cheaply); only their first two entries and lengths are used here.
+    """
+    p = Params()
+    p.dt = float(dt)
+    p.n2 = bvf ** 2                                     # L:383
+    p.two_rot = 2 * rot_earth                           # L:382
+    p.rad_earth = rad_earth
+    p.c8rot2 = 8 * rot_earth ** 2                       # L:491
+    f0 = 2 * rot_earth * np.sin(phi0)                   # L:535 (numpy scalar, as in the reference)
+    p.f0 = float(f0)
+    p.f0sq = float(f0 ** 2)                             # L:383 with scalar phi0
+    p.k2half = kappa ** 2 * .5                          # L:601
+    g01 = np.asarray(grid[:2], dtype=np.float64)
+    gs01 = np.asarray(grids[:2], dtype=np.float64)
+    p.dz_grid = float(np.diff(g01)[0])                  # L:349, 662
+    p.dz_grids = float(np.diff(gs01)[0])                # L:123 (grid := grids)
+    p.inv_dz_grid = 1.0 / p.dz_grid
+    p.inv_dz_grids = 1.0 / p.dz_grids
+    p.G = int(len(grids))
+    p.hprop = int(bool(hprop))
+    p.saturate_online = int(bool(saturate_online))
+    return p

@@ -1,0 +1,203 @@
+"""Device plumbing behind the drop-in functions of :mod:`msgwam_b200.libprop`.
+
+torch is used for device memory, streams and (in :mod:`msgwam_b200.distributed`) NCCL; all
+arithmetic is done by the CUDA kernels in ``csrc/`` through the C ABI.  There is no CPU path:
+without a CUDA device every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import Grid, Params, Rays, check, lib
+
+_vp = ctypes.c_void_p
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Engine:
+    """Per-process device context: scratch buffers cached by size, current-stream launches."""
+
+    _instance = None
+
+    @classmethod
+    def get(cls) -> "Engine":
+        if cls._instance is None:
+            cls._instance = cls()
+        return cls._instance
+
+    def __init__(self):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _cabi.MsgwamError("msgwam_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._work = {}
+        self._stage = {}
+        self._grid_cache = {}
+        self._derived = None
+        self.launches = 0          # kernels launched through this engine (bench.py reports it)
+
+    # ---- helpers -----------------------------------------------------------------------------
+    @property
+    def stream(self) -> _vp:
+        return _vp(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def is_dev(self, x) -> bool:
+        return isinstance(x, self.torch.Tensor) and x.is_cuda
+
+    def dev(self, x, n=None):
+        """float64 contiguous device tensor of length n (scalars are broadcast)."""
+        torch = self.torch
+        if isinstance(x, torch.Tensor):
+            t = x.to(device=self.device, dtype=torch.float64)
+        else:
+            a = np.asarray(x, dtype=np.float64)
+            if n is not None and a.ndim == 0:
+                return torch.full((n,), float(a), dtype=torch.float64, device=self.device)
+            t = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        if n is not None and t.ndim == 0:
+            t = t.expand(n)
+        return t.contiguous()
+
+    def empty(self, *shape):
+        return self.torch.empty(*shape, dtype=self.torch.float64, device=self.device)
+
+    def zeros(self, *shape):
+        return self.torch.zeros(*shape, dtype=self.torch.float64, device=self.device)
+
+    @staticmethod
+    def ptr(t) -> _vp:
+        return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+    def column_work(self, G: int):
+        """Deposit buffers D0|D1|D2 for the fused column step; zero on creation, kept zero by the
+        finish kernel."""
+        w = self._work.get(G)
+        if w is None:
+            w = self.zeros(int(lib.msgwam_column_work_doubles(G)))
+            self._work[G] = w
+        return w
+
+    def host_stage(self, n: int, G: int):
+        key = (n, G)
+        s = self._stage.get(key)
+        if s is None:
+            self._stage.clear()                 # one staging buffer at a time
+            s = self.empty(int(lib.msgwam_host_stage_doubles(n, G)))
+            self._stage[key] = s
+        return s
+
+    def grid_on_device(self, grid, grids, rhobar, pg):
+        """Device copies of the four background profiles, re-uploaded only when their values change."""
+        G = len(grids)
+        host = (np.ascontiguousarray(grid, dtype=np.float64), np.ascontiguousarray(grids, dtype=np.float64),
+                np.ascontiguousarray(np.broadcast_to(np.asarray(rhobar, dtype=np.float64), (G,))),
+                np.ascontiguousarray(pg, dtype=np.float64).reshape(2, G))
+        c = self._grid_cache.get(G)
+        if c is not None and all(np.array_equal(a, b) for a, b in zip(c[0], host)):
+            return c[1]
+        devs = tuple(self.torch.from_numpy(a.copy()).to(self.device) for a in host)
+        self._grid_cache[G] = (tuple(a.copy() for a in host), devs)
+        return devs
+
+    def grid_struct(self, devs) -> Grid:
+        return Grid(self.ptr(devs[0]), self.ptr(devs[1]), self.ptr(devs[2]), self.ptr(devs[3]))
+
+    def derived_statics(self, phi, dkk, dll, two_rot):
+        """ff = 2*ROT*sin(phi), pkl = dkk*dll on the device; cached on (storage, version) of the inputs."""
+        key = tuple((t.data_ptr(), t._version, t.numel()) for t in (phi, dkk, dll)) + (two_rot,)
+        if self._derived is not None and self._derived[0] == key:
+            return self._derived[1], self._derived[2]
+        n = phi.numel()
+        ff, pkl = self.empty(n), self.empty(n)
+        check(lib.msgwam_derive_statics(self.ptr(phi), self.ptr(dkk), self.ptr(dll), self.ptr(ff), self.ptr(pkl),
+                                        n, two_rot, self.stream), "msgwam_derive_statics")
+        self.launches += 1
+        self._derived = (key, ff, pkl)
+        return ff, pkl
+
+    # ---- fused column step on device tensors ---------------------------------------------------
+    def column_step(self, p: Params, state, dkk, dll, uu, vv, grid_devs, rr_out=None, mm_out=None,
+                    reduce_fn=None):
+        """state: 9 device tensors (reference order).  Returns (rr_new, mm_new, uu_new, vv_new).
+
+        reduce_fn(tensor) -- optional in-place all-reduce of the deposit buffers (multi-GPU)."""
+        dens, lam, phi, rr, drr, kk, ll, mm, dmm = state
+        n = rr.numel()
+        ff, pkl = self.derived_statics(phi, dkk, dll, p.two_rot)
+        rays = Rays()
+        for k, t in (("dens", dens), ("phi", phi), ("rr", rr), ("drr", drr), ("kk", kk), ("ll", ll), ("mm", mm),
+                     ("dmm", dmm), ("dkk", dkk), ("dll", dll), ("ff", ff), ("pkl", pkl)):
+            setattr(rays, k, t.data_ptr())
+        g = self.grid_struct(grid_devs)
+        work = self.column_work(p.G)
+        rr_out = self.empty(n) if rr_out is None else rr_out
+        mm_out = self.empty(n) if mm_out is None else mm_out
+        uu_out, vv_out = self.empty(p.G), self.empty(p.G)
+        s = self.stream
+        if reduce_fn is None:
+            check(lib.msgwam_column_step(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
+                                         self.ptr(mm_out), self.ptr(uu_out), self.ptr(vv_out), s), "msgwam_column_step")
+        else:
+            nc = p.G - 1
+            check(lib.msgwam_column_pass_a(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), s), "msgwam_column_pass_a")
+            reduce_fn(work[:4 * nc])
+            check(lib.msgwam_column_pass_b(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
+                                           self.ptr(mm_out), s), "msgwam_column_pass_b")
+            reduce_fn(work[4 * nc:])
+            check(lib.msgwam_column_finish(p, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(uu_out),
+                                           self.ptr(vv_out), s), "msgwam_column_finish")
+        self.launches += 3
+        return rr_out, mm_out, uu_out, vv_out
+
+    # ---- general right-hand side on device tensors ----------------------------------------------
+    def rhs_general(self, p: Params, state, statics, uu, vv, grid_devs, reduce_fn=None):
+        """All 11 tendencies (9 ray arrays + du, dv) and the deposit, every branch of rhs_default."""
+        n = state[0].numel()
+        rays = Rays()
+        for k, t in zip(("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm"), state):
+            setattr(rays, k, t.data_ptr())
+        for k, t in zip(("dkk", "dll", "rr_mm_area"), statics):
+            setattr(rays, k, t.data_ptr())
+        g = self.grid_struct(grid_devs)
+        tend = [self.empty(n) for _ in range(9)]
+        tp = (_vp * 9)(*[t.data_ptr() for t in tend])
+        proj = self.zeros(2, p.G - 1)
+        s = self.stream
+        check(lib.msgwam_rhs_rays(p, rays, n, g, self.ptr(uu), self.ptr(vv), tp, self.ptr(proj), s), "msgwam_rhs_rays")
+        if reduce_fn is not None:
+            reduce_fn(proj)
+        du, dv = self.empty(p.G), self.empty(p.G)
+        check(lib.msgwam_grid_tendency(p, g, self.ptr(uu), self.ptr(vv), self.ptr(proj), self.ptr(du), self.ptr(dv), s),
+              "msgwam_grid_tendency")
+        self.launches += 3
+        return tend, du, dv, proj
+
+    def rk3_general(self, p: Params, state, statics, uu, vv, grid_devs, reduce_fn=None):
+        """RK3 with rhs_default for any mode: three stages of rhs_general + low-storage updates."""
+        x = list(state)
+        n = x[0].numel()
+        q = [self.empty(n) for _ in range(9)]
+        qu, qv = self.empty(p.G), self.empty(p.G)
+        s = self.stream
+        for stage in range(3):
+            tend, du, dv, _ = self.rhs_general(p, x, statics, uu, vv, grid_devs, reduce_fn)
+            xn = []
+            for f in range(9):
+                o = self.empty(n)
+                check(lib.msgwam_rk_update(stage, p.dt, self.ptr(tend[f]), self.ptr(q[f]), self.ptr(x[f]), self.ptr(o), n, s),
+                      "msgwam_rk_update")
+                xn.append(o)
+            un, vn = self.empty(p.G), self.empty(p.G)
+            check(lib.msgwam_rk_update(stage, p.dt, self.ptr(du), self.ptr(qu), self.ptr(uu), self.ptr(un), p.G, s), "msgwam_rk_update")
+            check(lib.msgwam_rk_update(stage, p.dt, self.ptr(dv), self.ptr(qv), self.ptr(vv), self.ptr(vn), p.G, s), "msgwam_rk_update")
+            self.launches += 11
+            x, uu, vv = xn, un, vn
+        return x, uu, vv

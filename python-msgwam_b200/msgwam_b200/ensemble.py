@@ -1,0 +1,159 @@
+"""Device-resident, optionally sharded ray store.
+
+The drop-in ``libprop.RK3`` takes and returns the reference's 11-slot state vector; for large
+ensembles that means moving every field over PCIe each step.  ``RayEnsemble`` keeps the
+structure-of-arrays store (9 state fields, 3 statics, 2 derived statics) in HBM and advances it in
+place with the same kernels.  With ``torch.distributed`` initialised (one process per GPU, NCCL) each
+rank owns a contiguous slice of the rays; the only exchange is the all-reduce of the deposited flux
+(2 x (G-1) doubles per RK stage, batched into two calls per step), after which every rank advances its
+replica of the mean flow identically.
+
+Ray deletion (``compact``) has no counterpart in the reference, whose only related predicate is
+``out_of_domain`` in wave_projection (L:129-130): rays outside the deposit domain, or with
+|m| >= m_crit (critical-level pile-up), are removed between steps by a stable stream compaction.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import check, lib
+from ._engine import Engine
+
+STATE = ("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm")
+STATICS = ("dkk", "dll", "rr_mm_area")
+_vp = ctypes.c_void_p
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class RayEnsemble:
+    def __init__(self, state, dkk, dll, rr_mm_area, uu, vv, grid, grids, rhobar, pressure_gradient, *,
+                 bvf, phi0, kappa=1.0, saturate_online=False, hprop=False, distributed=None):
+        """state: the 9 per-ray arrays of this rank's slice (numpy or torch); grid fields are replicated."""
+        self.eng = Engine.get()
+        eng = self.eng
+        n = int(np.size(state[3])) if not hasattr(state[3], "numel") else int(state[3].numel())
+        self.n = n
+        self.cap = max(n, 1)
+        # one slab per buffer so that compaction can ping-pong between two of them
+        self._slab = eng.empty(len(STATE) + len(STATICS) + 2, self.cap)
+        self._slab2 = None
+        names = STATE + STATICS
+        for i, (nm, a) in enumerate(zip(names, list(state) + [dkk, dll, rr_mm_area])):
+            self._slab[i, :n].copy_(eng.dev(a, n))
+        self.cfg = dict(bvf=bvf, phi0=phi0, kappa=kappa, saturate_online=saturate_online, hprop=hprop)
+        self.grid_host, self.grids_host = np.asarray(grid, dtype=np.float64), np.asarray(grids, dtype=np.float64)
+        self.G = len(self.grids_host)
+        self.grid_devs = tuple(eng.dev(a) for a in (self.grid_host, self.grids_host,
+                                                    np.broadcast_to(np.asarray(rhobar, dtype=np.float64), (self.G,)),
+                                                    np.asarray(pressure_gradient, dtype=np.float64).reshape(2, self.G)))
+        self.uu, self.vv = eng.dev(uu, self.G).clone(), eng.dev(vv, self.G).clone()
+        self._uu2, self._vv2 = eng.empty(self.G), eng.empty(self.G)
+        self.work = eng.zeros(int(lib.msgwam_column_work_doubles(self.G)))
+        self.dist = _dist() if distributed is None else (distributed or None)
+        self._derive()
+
+    @classmethod
+    def from_scenario(cls, sc, **kw):
+        return cls(sc.state, sc.dkk, sc.dll, sc.rr_mm_area, sc.uu, sc.vv, sc.grid, sc.grids, sc.rhobar,
+                   sc.pressure_gradient, bvf=sc.model["bvf"], phi0=sc.model["phi0"], kappa=sc.model.get("kappa", 1.0),
+                   saturate_online=sc.model.get("saturate_online", False), hprop=sc.hprop, **kw)
+
+    # ---- views ------------------------------------------------------------------------------------
+    def field(self, name):
+        names = STATE + STATICS + ("ff", "pkl")
+        return self._slab[names.index(name), :self.n]
+
+    def _derive(self):
+        eng = self.eng
+        check(lib.msgwam_derive_statics(eng.ptr(self.field("phi")), eng.ptr(self.field("dkk")), eng.ptr(self.field("dll")),
+                                        eng.ptr(self.field("ff")), eng.ptr(self.field("pkl")), self.n,
+                                        2 * _cabi.ROT_EARTH_DEFAULT, eng.stream), "msgwam_derive_statics")
+        eng.launches += 1
+
+    def params(self, dt) -> _cabi.Params:
+        return _cabi.snapshot_params(dt, grid=self.grid_host, grids=self.grids_host, **self.cfg)
+
+    def _rays(self) -> _cabi.Rays:
+        r = _cabi.Rays()
+        for nm in STATE + STATICS + ("ff", "pkl"):
+            setattr(r, nm, self.field(nm).data_ptr())
+        return r
+
+    def _reduce(self, t):
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(t)
+
+    # ---- stepping ---------------------------------------------------------------------------------
+    def step(self, dt, nsteps=1):
+        """Advance rays and mean flow in place by nsteps RK3 steps (reference RK3 + rhs_default semantics)."""
+        eng = self.eng
+        p = self.params(dt)
+        g = eng.grid_struct(self.grid_devs)
+        column = not p.hprop and not p.saturate_online
+        nc = self.G - 1
+        for _ in range(nsteps):
+            if column:
+                rays = self._rays()
+                s = eng.stream
+                rr, mm = self.field("rr"), self.field("mm")
+                check(lib.msgwam_column_pass_a(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work), s),
+                      "msgwam_column_pass_a")
+                self._reduce(self.work[:4 * nc])
+                check(lib.msgwam_column_pass_b(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
+                                               eng.ptr(rr), eng.ptr(mm), s), "msgwam_column_pass_b")
+                self._reduce(self.work[4 * nc:])
+                check(lib.msgwam_column_finish(p, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
+                                               eng.ptr(self._uu2), eng.ptr(self._vv2), s), "msgwam_column_finish")
+                eng.launches += 3
+                self.uu, self._uu2 = self._uu2, self.uu
+                self.vv, self._vv2 = self._vv2, self.vv
+            else:
+                state = [self.field(nm) for nm in STATE]
+                st = [self.field(nm) for nm in STATICS]
+                x, uu, vv = eng.rk3_general(p, state, st, self.uu, self.vv, self.grid_devs, self._reduce)
+                for nm, t in zip(STATE, x):
+                    self.field(nm).copy_(t)
+                self.uu, self.vv = uu, vv
+                self._derive()
+
+    # ---- deletion ---------------------------------------------------------------------------------
+    def compact(self, dt=0.0, m_crit=float("inf")) -> int:
+        """Delete rays outside the deposit domain (L:129-130) or with |m| >= m_crit.  Returns survivors."""
+        eng = self.eng
+        torch = eng.torch
+        p = self.params(dt)
+        n = self.n
+        if n == 0:
+            return 0
+        keep = torch.empty(n + 16, dtype=torch.uint8, device=eng.device)
+        check(lib.msgwam_flag_rays(p, n, eng.ptr(self.field("rr")), eng.ptr(self.field("drr")), eng.ptr(self.field("mm")),
+                                   float(m_crit), _vp(keep.data_ptr()), eng.stream), "msgwam_flag_rays")
+        if self._slab2 is None:
+            self._slab2 = eng.empty(*self._slab.shape)
+        nf = self._slab.shape[0]
+        ins = (_vp * nf)(*[self._slab[f].data_ptr() for f in range(nf)])
+        outs = (_vp * nf)(*[self._slab2[f].data_ptr() for f in range(nf)])
+        count = torch.zeros(1, dtype=torch.int64, device=eng.device)
+        scratch = torch.empty(int(lib.msgwam_compact_scratch_bytes(n)), dtype=torch.uint8, device=eng.device)
+        check(lib.msgwam_compact(n, _vp(keep.data_ptr()), nf, ins, outs, _vp(count.data_ptr()), _vp(scratch.data_ptr()),
+                                 eng.stream), "msgwam_compact")
+        eng.launches += 4
+        self._slab, self._slab2 = self._slab2, self._slab
+        self.n = int(count.item())
+        return self.n
+
+    # ---- export -----------------------------------------------------------------------------------
+    def to_var(self):
+        """The reference's 11-slot state vector (numpy copies)."""
+        out = np.empty(11, dtype=object)
+        for i, nm in enumerate(STATE):
+            out[i] = self.field(nm).cpu().numpy()
+        out[9], out[10] = self.uu.cpu().numpy(), self.vv.cpu().numpy()
+        return out

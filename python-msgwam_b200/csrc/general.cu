@@ -133,25 +133,29 @@ struct ProjArgs {
     double *out;
 };
 
+// dynamic shared memory: warp windows (always) | grid copy | histogram (when they fit)
 __global__ void __launch_bounds__(NT) project_kernel(const ProjArgs a)
 {
     extern __shared__ double sm[];
     const int nc = a.ng - 1;
     const int ncomp = a.var == 0 ? 2 : 1;
+    double *wins = sm + ((reinterpret_cast<uintptr_t>(sm) & 8) ? 1 : 0);
+    double *rest = wins + (NT / 32) * WIN_DOUBLES;
     double *h0, *h1;
     const double *g;
+    Window win;
+    window_init(win, wins + (size_t)(threadIdx.x >> 5) * WIN_DOUBLES);
     if (a.use_smem) {
-        double *gs = sm; h0 = sm + a.ng; h1 = h0 + nc;
+        double *gs = rest; h0 = rest + a.ng; h1 = h0 + nc;
         for (int j = threadIdx.x; j < a.ng; j += NT) gs[j] = a.grid[j];
         for (int j = threadIdx.x; j < 2 * nc; j += NT) h0[j] = 0.0;
-        __syncthreads();
         g = gs;
     } else {
         // grids too large for shared memory: accumulate straight into the output.  The second
-        // component of single-component variants goes to a dummy slot that is never non-zero.
+        // component of single-component variants is identically zero and lands on the first.
         g = a.grid; h0 = a.out; h1 = a.out + (ncomp == 2 ? nc : 0);
     }
-    Acc acc; acc.clear();
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (NT / 32);
     const int64_t gw = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
@@ -185,9 +189,9 @@ __global__ void __launch_bounds__(NT) project_kernel(const ProjArgs a)
                 }
             }
         }
-        deposit_cells(ok, nlow, nup, rl, ru, psv, v0, v1, a.dz, a.rdz, g, acc, h0, h1);
+        deposit_cells(ok, nlow, nup, rl, ru, psv, v0, v1, a.dz, a.rdz, g, win, h0, h1);
     }
-    flush_acc(acc, h0, h1);
+    window_flush(win, h0, h1);
     if (a.use_smem) {
         __syncthreads();
         for (int j = threadIdx.x; j < ncomp * nc; j += NT) {
@@ -366,6 +370,23 @@ inline int grid_for(int64_t n, int threads, int per_sm)
     return (int)b;
 }
 
+int launch_project(ProjArgs &q, int64_t n, cudaStream_t s)
+{
+    const size_t win_bytes = ((size_t)(NT / 32) * WIN_DOUBLES + 2) * sizeof(double);
+    const size_t full = win_bytes + (size_t)(q.ng + 2 * (q.ng - 1)) * sizeof(double);
+    q.use_smem = full <= (size_t)g_smem;
+    const size_t bytes = q.use_smem ? full : win_bytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    // few, fat CTAs: each one carries a private histogram that is merged with global atomics at the end
+    project_kernel<<<grid_for(n, NT * 8, 2), NT, bytes, s>>>(q);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
@@ -394,14 +415,7 @@ int msgwam_rhs_rays(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t
     q.ma = rays->mm; q.mb = rays->dmm; q.dkk = rays->dkk; q.dll = rays->dll; q.dmm = rays->dmm;
     q.grid = grid->grids; q.ng = p->G; q.dz = p->dz_grids; q.rdz = p->inv_dz_grids; q.out = d_proj;
     if (n > 0) {
-        const size_t bytes = (size_t)(q.ng + 2 * (q.ng - 1)) * sizeof(double);
-        q.use_smem = bytes <= (size_t)g_smem;
-        if (q.use_smem) {
-            cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem);
-            if (e != cudaSuccess) return (int)e;
-        }
-        project_kernel<<<grid_for(n, NT * 4, 4), NT, q.use_smem ? bytes : 0, s>>>(q);
-        return (int)cudaGetLastError();
+        return launch_project(q, n, s);
     }
     return 0;
 }
@@ -465,14 +479,7 @@ int msgwam_wave_projection(int32_t var, const msgwam_params_t *p, int64_t n, con
         project_iface_kernel<<<grid_for(n, NT, 8), NT, 0, s>>>(q);
         return (int)cudaGetLastError();
     }
-    const size_t bytes = (size_t)(ng + 2 * (ng - 1)) * sizeof(double);
-    q.use_smem = bytes <= (size_t)g_smem;
-    if (q.use_smem) {
-        e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    project_kernel<<<grid_for(n, NT * 4, 4), NT, q.use_smem ? bytes : 0, s>>>(q);
-    return (int)cudaGetLastError();
+    return launch_project(q, n, s);
 }
 
 int msgwam_saturation(const msgwam_params_t *p, int64_t n, int32_t direct, const double *d_dens, const double *d_rr,

@@ -61,7 +61,10 @@ class Engine:
             a = np.asarray(x, dtype=np.float64)
             if n is not None and a.ndim == 0:
                 return torch.full((n,), float(a), dtype=torch.float64, device=self.device)
-            t = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            a = np.ascontiguousarray(a)
+            if not a.flags.writeable:
+                a = a.copy()
+            t = torch.from_numpy(a).to(self.device)
         if n is not None and t.ndim == 0:
             t = t.expand(n)
         return t.contiguous()

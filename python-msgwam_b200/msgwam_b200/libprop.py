@@ -262,7 +262,8 @@ def _grid_tend(which, wind, pm_flux_gradient):
     pg = eng.dev(np.asarray(pressure_gradient, dtype=np.float64)[which])
     out = eng.empty(G)
     f0 = float(2 * ROT_EARTH * np.sin(model_config['phi0']))
-    check(lib.msgwam_mean_flow_tendency(which, f0, G, eng.ptr(eng.dev(wind, G)), eng.ptr(eng.dev(pm_flux_gradient, G)),
+    tw, tg = eng.dev(wind, G), eng.dev(pm_flux_gradient, G)      # keep the temporaries alive until the launch is queued
+    check(lib.msgwam_mean_flow_tendency(which, f0, G, eng.ptr(tw), eng.ptr(tg),
                                         eng.ptr(rho), eng.ptr(pg), eng.ptr(out), eng.stream), "msgwam_mean_flow_tendency")
     eng.launches += 1
     return _out(eng, out, like_dev)

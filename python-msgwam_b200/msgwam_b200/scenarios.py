@@ -165,7 +165,10 @@ def column_ensemble(n: int, seed: int = 1234, ngrid: int = 1001, sheared: bool =
         f0 = 2 * ROT_EARTH * np.sin(phi0)
         omh = np.sqrt((NN ** 2 * (kk ** 2 + ll ** 2) + f0 ** 2 * mm ** 2) / (kk ** 2 + ll ** 2 + mm ** 2))
         rho_ray = np.interp(rr, grids, rhobar)
-        dens = amplitude ** 2 * rho_ray / 2 * omh / mm ** 2 / (omh ** 2 - f0 ** 2) * NN ** 2 / dkk / dll / dmm
+        # ... shared among the ray volumes that overlap one grid cell, so that the ensemble as a whole (not each
+        # of its n members) carries the amplitude `amplitude` relative to static instability
+        per_cell = max(1.0, n * float(np.mean(drr)) / ztop_rays)
+        dens = amplitude ** 2 * rho_ray / 2 * omh / mm ** 2 / (omh ** 2 - f0 ** 2) * NN ** 2 / dkk / dll / dmm / per_cell
     pg = _geostrophic_pg(rhobar, phi0, uu, vv)
     state = [dens, lam, phi, rr, drr, kk, ll, mm, dmm]
     stat = [dkk, dll, area]

@@ -68,7 +68,7 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
     if (ok) {
         const int lane = threadIdx.x & 31;
         for (int c = nlow; c < nup; ++c) {
-            const double zmin = fmax(g[c], rl), zmax = fmin(g[c + 1], ru);
+            const double zmin = dmax(g[c], rl), zmax = dmin(g[c + 1], ru);
             const double t = mul(div_inv(fabs(sub(zmax, zmin)), dz, rdz), psv);
             const double t0 = mul(t, v0), t1 = mul(t, v1);
             if (fits) {

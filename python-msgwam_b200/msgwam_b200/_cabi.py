@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsgwam_b200.so")
+# MSGWAM_B200_LIB: developer override to time alternative builds of the same sources (tools/)
+LIB_PATH = os.environ.get("MSGWAM_B200_LIB") or os.path.join(_HERE, "libmsgwam_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_void_p = ctypes.c_void_p

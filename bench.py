@@ -169,7 +169,7 @@ def run_ours(args, rank, local_rank, world):
         check(lib.msgwam_column_finish(p, g, P(ens.uu), P(ens.vv), P(ens.work), P(uu_out), P(vv_out), eng.stream), "finish")
 
     def step():          # out of place: every timed step does identical work on the same input state
-        pass_a(); reduce_(ens.work[:4 * nc]); pass_b(); reduce_(ens.work[4 * nc:]); finish()
+        pass_a(); reduce_(ens.work[:4 * nc]); pass_b(); reduce_(ens.work[4 * nc:6 * nc]); finish()
 
     def barrier():
         torch.cuda.synchronize()
@@ -204,7 +204,7 @@ def run_ours(args, rank, local_rank, world):
         flush.zero_()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record(); pass_a(); e[1].record(); reduce_(ens.work[:4 * nc]); pass_b_start = torch.cuda.Event(enable_timing=True)
-        pass_b_start.record(); pass_b(); e[2].record(); reduce_(ens.work[4 * nc:]); fin0 = torch.cuda.Event(enable_timing=True)
+        pass_b_start.record(); pass_b(); e[2].record(); reduce_(ens.work[4 * nc:6 * nc]); fin0 = torch.cuda.Event(enable_timing=True)
         fin0.record(); finish(); e[3].record()
         torch.cuda.synchronize()
         ka.append(e[0].elapsed_time(e[1])); kb.append(pass_b_start.elapsed_time(e[2])); kf.append(fin0.elapsed_time(e[3]))

@@ -97,9 +97,14 @@ int msgwam_derive_statics(const double *d_phi, const double *d_dkk, const double
  *   [multi-GPU: all-reduce D2: 2*(G-1) doubles]
  *   finish : u3, v3 from u0, D0, D1, D2; zeroes the deposit buffers for the next step
  * d_work: msgwam_column_work_doubles(G) doubles, zero-initialised by the caller once; layout
- * D0 (2,G-1) | D1 (2,G-1) | D2 (2,G-1).  rr_out/mm_out may alias rays->rr / rays->mm.
+ * D0 (2,G-1) | D1 (2,G-1) | D2 (2,G-1) | shear tables and saved mean-flow stage (internal).
+ * rr_out/mm_out may alias rays->rr / rays->mm.  msgwam_column_pass_b first launches a one-CTA kernel that
+ * advances the mean-flow half of RK stages 1-2 and builds the shear tables the sweep interpolates.
  */
 int64_t msgwam_column_work_doubles(int32_t G);
+/* largest G (= len(grids)) the fused column kernels accept on this device: the shear tables of the three
+ * RK stages must fit in shared memory.  Larger grids take msgwam_rhs_rays stage by stage. */
+int32_t msgwam_column_max_levels(void);
 int msgwam_column_pass_a(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
                          const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
                          double *d_work, void *stream);
@@ -109,11 +114,17 @@ int msgwam_column_pass_b(const msgwam_params_t *p, const msgwam_rays_t *rays, in
 int msgwam_column_finish(const msgwam_params_t *p, const msgwam_grid_t *grid,
                          const double *d_uu, const double *d_vv, double *d_work,
                          double *d_uu_out, double *d_vv_out, void *stream);
-/* single-GPU convenience: pass A, pass B, finish on `stream` */
+/* single GPU: two launches -- the mean-flow chain and the finish run as the tails of the sweeps, in the last
+ * CTA to retire */
 int msgwam_column_step(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
                        const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
                        double *d_work, double *d_rr_out, double *d_mm_out,
                        double *d_uu_out, double *d_vv_out, void *stream);
+
+/* test hook: cg_rr exactly as the fused column kernels evaluate it (shared reciprocals, one range check),
+ * so that tests can compare it bit for bit with the library route used by msgwam_pointwise */
+int msgwam_debug_cg_rr_fast(const double *d_kk, const double *d_ll, const double *d_mm, const double *d_ff,
+                            double n2, double *d_out, int64_t n, void *stream);
 
 /* ---- general single-stage right-hand side  (replaces rhs_default L:618-676, every branch:
  *      HPROP on/off, saturate_online on/off).  d_tend[9] receive the nine ray tendencies in

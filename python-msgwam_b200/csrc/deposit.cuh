@@ -7,26 +7,31 @@
 // lane adds its ray's contributions to its own column with a plain 128-bit load/add/store -- no
 // atomics, no bank conflicts, no cross-lane traffic.  Only when the cells touched by the warp leave
 // the window (every ~100 iterations for an ordered ensemble) or at the end of the sweep is the window
-// flushed: one shuffle reduction per cell, one lane adds to the CTA histogram.  Warps whose lanes are
-// scattered over more than WIN cells (unordered rays) bypass the window and add to the histogram
-// directly, where collisions are then rare.  The CTA histogram goes to HBM with one fp64 RED per
-// non-zero cell when the CTA retires.
+// flushed: one shuffle reduction per cell, then WIN lanes add one cell each to the global deposit with
+// fp64 RED operations (fire-and-forget L2 atomics).  Warps whose lanes are scattered over more than WIN
+// cells (unordered rays) bypass the window and add to a CTA histogram in shared memory, where collisions
+// are then rare; a CTA that used its histogram merges it into the global deposit when it retires.
 #pragma once
 #include "common.cuh"
 #include <limits.h>
 
 namespace mw {
 
-constexpr int WIN = 8;                         // cells per warp window
-constexpr int WIN_DOUBLES = WIN * 32 * 2;      // shared-memory doubles per warp and deposit target
+constexpr int WIN_DEFAULT = 8;                 // cells per warp window
 
-struct Window {
+template <int WIN>
+struct WindowT {
+    static constexpr int CELLS = WIN;
+    static constexpr int DOUBLES = WIN * 32 * 2;   // shared-memory doubles per warp and deposit target
     double2 *cell;   // this warp's [WIN][32] running sums
     int wb;          // grid cell of slot 0 (meaningful when live)
     int live;        // the window holds sums
 };
+using Window = WindowT<WIN_DEFAULT>;
+constexpr int WIN_DOUBLES = Window::DOUBLES;
 
-__device__ __forceinline__ void window_init(Window &w, double *base)
+template <int WIN>
+__device__ __forceinline__ void window_init(WindowT<WIN> &w, double *base)
 {
     w.cell = reinterpret_cast<double2 *>(base);
     w.wb = 0; w.live = 0;
@@ -35,28 +40,64 @@ __device__ __forceinline__ void window_init(Window &w, double *base)
     for (int s = 0; s < WIN; ++s) w.cell[s * 32 + lane] = make_double2(0.0, 0.0);
 }
 
-// warp-collective: column sums of the window go to the histogram h0/h1 (shared or global memory)
-__device__ __forceinline__ void window_flush(Window &w, double *h0, double *h1)
+// warp-collective: column sums of the window go to h0/h1 (global memory in the sweeps).
+// Lane l owns slot l % WIN and sums every (32 / WIN)-th column of it straight from shared memory (the
+// column index is rotated by the slot so that the slots fall into different banks); the 32 / WIN partial
+// sums of a slot meet in a few shuffles and WIN lanes issue one atomic each, concurrently.
+template <int WIN>
+__device__ __noinline__ void window_flush_slow(double2 *cell, int wb, double *h0, double *h1)
+{
+    constexpr int GROUPS = 32 / WIN;
+    const int lane = threadIdx.x & 31;
+    const int s = lane % WIN, g = lane / WIN;
+    __syncwarp();
+    double ax = 0.0, ay = 0.0;
+    if (g < GROUPS) {
+        for (int col = g; col < 32; col += GROUPS) {
+            const double2 a = cell[s * 32 + ((col + s) & 31)];
+            ax += a.x; ay += a.y;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 1; k < GROUPS; ++k) {
+        const double bx = __shfl_sync(FULL_MASK, ax, (lane + k * WIN) & 31);
+        const double by = __shfl_sync(FULL_MASK, ay, (lane + k * WIN) & 31);
+        if (lane < WIN) { ax += bx; ay += by; }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < WIN; ++s2) cell[s2 * 32 + lane] = make_double2(0.0, 0.0);
+    __syncwarp();
+    if (lane < WIN && (ax != 0.0 || ay != 0.0)) { atomicAdd(h0 + wb + lane, ax); atomicAdd(h1 + wb + lane, ay); }
+}
+
+template <int WIN>
+__device__ __forceinline__ void window_flush(WindowT<WIN> &w, double *h0, double *h1)
 {
     if (!w.live) return;                                        // warp-uniform
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int s = 0; s < WIN; ++s) {
-        const double2 a = w.cell[s * 32 + lane];
-        w.cell[s * 32 + lane] = make_double2(0.0, 0.0);
-        const double x0 = warp_sum(a.x), x1 = warp_sum(a.y);
-        if (lane == 0 && (x0 != 0.0 || x1 != 0.0)) { atomicAdd(h0 + w.wb + s, x0); atomicAdd(h1 + w.wb + s, x1); }
-    }
+    window_flush_slow<WIN>(w.cell, w.wb, h0, h1);
     w.live = 0;
+}
+
+// overlap weight of [rl, ru] with cell c times psv (L:157-162): |min(g[c+1], ru) - max(g[c], rl)| / dz * psv
+__device__ __forceinline__ double cell_weight(int c, double rl, double ru, double psv, double dz, double rdz,
+                                              const double *__restrict__ g)
+{
+    const double zmin = dmax(g[c], rl), zmax = dmin(g[c + 1], ru);
+    return mul(div_inv(fabs(sub(zmax, zmin)), dz, rdz), psv);
 }
 
 // Overlap weights of one ray volume [rl, ru] with cells [nlow, nup) times (psv * v0, psv * v1),
 // L:156-163:  w = |min(grid[c+1], ru) - max(grid[c], rl)| / dz;  out[c] += w * psv * v.
 // `ok` is false for lanes without a ray or with an out-of-domain ray; all 32 lanes must call.
+// h0/h1: where window flushes go (the global deposit in the sweeps); s0/s1 + used: the CTA histogram for
+// scattered warps and its "dirty" flag (pass s0 = h0, s1 = h1, used = nullptr to add there directly).
+template <int WIN>
 __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double rl, double ru,
                                               double psv, double v0, double v1,
                                               double dz, double rdz, const double *__restrict__ g,
-                                              Window &w, double *h0, double *h1)
+                                              WindowT<WIN> &w, double *h0, double *h1,
+                                              double *s0, double *s1, int *used)
 {
     ok = ok && (nup > nlow);
     const int lo = __reduce_min_sync(FULL_MASK, ok ? nlow : INT_MAX);
@@ -64,21 +105,38 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
     const int hi = __reduce_max_sync(FULL_MASK, ok ? nup : INT_MIN);
     const bool fits = (hi - lo) <= WIN;
     if (w.live && (!fits || lo < w.wb || hi > w.wb + WIN)) window_flush(w, h0, h1);
-    if (fits && !w.live) { w.wb = lo; w.live = 1; }
-    if (ok) {
-        const int lane = threadIdx.x & 31;
-        for (int c = nlow; c < nup; ++c) {
-            const double zmin = dmax(g[c], rl), zmax = dmin(g[c + 1], ru);
-            const double t = mul(div_inv(fabs(sub(zmax, zmin)), dz, rdz), psv);
-            const double t0 = mul(t, v0), t1 = mul(t, v1);
-            if (fits) {
-                double2 *p = w.cell + (c - w.wb) * 32 + lane;
-                double2 a = *p;
-                a.x = add(a.x, t0); a.y = add(a.y, t1);
-                *p = a;
-            } else {
-                atomicAdd(h0 + c, t0);
-                atomicAdd(h1 + c, t1);
+    if (fits) {
+        if (!w.live) { w.wb = lo; w.live = 1; }
+        if (ok) {
+            // private column of the warp window: plain load / add / store.  The first four cells are
+            // unrolled so that their weight computations overlap (a ray volume rarely spans more).
+            double2 *col = w.cell + (nlow - w.wb) * 32 + (threadIdx.x & 31);
+            double t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = (nlow + k < nup) ? cell_weight(nlow + k, rl, ru, psv, dz, rdz, g) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (nlow + k < nup) {
+                    double2 a = col[k * 32];
+                    a.x = add(a.x, mul(t[k], v0)); a.y = add(a.y, mul(t[k], v1));
+                    col[k * 32] = a;
+                }
+            }
+            for (int c = nlow + 4; c < nup; ++c) {
+                const double tc = cell_weight(c, rl, ru, psv, dz, rdz, g);
+                double2 a = col[(c - nlow) * 32];
+                a.x = add(a.x, mul(tc, v0)); a.y = add(a.y, mul(tc, v1));
+                col[(c - nlow) * 32] = a;
+            }
+        }
+    } else {
+        // scattered lanes (unordered rays): few collisions, add to the CTA histogram directly
+        if (used != nullptr && (threadIdx.x & 31) == 0) *used = 1;
+        if (ok) {
+            for (int c = nlow; c < nup; ++c) {
+                const double tc = cell_weight(c, rl, ru, psv, dz, rdz, g);
+                atomicAdd(s0 + c, mul(tc, v0));
+                atomicAdd(s1 + c, mul(tc, v1));
             }
         }
     }

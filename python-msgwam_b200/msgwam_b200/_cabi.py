@@ -52,10 +52,12 @@ SIGNATURES = {
     "msgwam_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "msgwam_derive_statics": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _dbl, _vp]),
     "msgwam_column_work_doubles": (_i64, [_i32]),
+    "msgwam_column_max_levels": (_i32, []),
     "msgwam_column_pass_a": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp]),
     "msgwam_column_pass_b": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_column_finish": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_column_step": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "msgwam_debug_cg_rr_fast": (ctypes.c_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _i64, _vp]),
     "msgwam_rhs_rays": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp]),
     "msgwam_grid_tendency": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_mean_flow_tendency": (ctypes.c_int, [_i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -154,7 +154,7 @@ class Engine:
             reduce_fn(work[:4 * nc])
             check(lib.msgwam_column_pass_b(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
                                            self.ptr(mm_out), s), "msgwam_column_pass_b")
-            reduce_fn(work[4 * nc:])
+            reduce_fn(work[4 * nc:6 * nc])
             check(lib.msgwam_column_finish(p, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(uu_out),
                                            self.ptr(vv_out), s), "msgwam_column_finish")
         self.launches += 3

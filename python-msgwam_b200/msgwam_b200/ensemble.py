@@ -108,7 +108,7 @@ class RayEnsemble:
                 self._reduce(self.work[:4 * nc])
                 check(lib.msgwam_column_pass_b(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
                                                eng.ptr(rr), eng.ptr(mm), s), "msgwam_column_pass_b")
-                self._reduce(self.work[4 * nc:])
+                self._reduce(self.work[4 * nc:6 * nc])
                 check(lib.msgwam_column_finish(p, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
                                                eng.ptr(self._uu2), eng.ptr(self._vv2), s), "msgwam_column_finish")
                 eng.launches += 3

@@ -248,3 +248,37 @@ def test_empty_and_tiny_ensembles(lprop):
     got, want = lprop.RK3(sc.dt, empty), oracle.Oracle(cfg).RK3(sc.dt, empty)
     assert got[3].shape == (0,)
     assert np.array_equal(got[9], want[9]) and np.array_equal(got[10], want[10])
+
+
+def test_fused_cg_rr_is_bit_identical_to_the_library_route(lprop):
+    """The column kernels evaluate cg_rr with shared reciprocals and a hand-rolled IEEE sqrt/division
+    (csrc/column_step.cu: cg_rr_fast).  It must round exactly like __ddiv_rn/__dsqrt_rn, i.e. like numpy."""
+    import ctypes
+    import torch
+    from msgwam_b200._cabi import check, lib
+    from msgwam_b200._engine import Engine
+    eng = Engine.get()
+    rng = np.random.default_rng(99)
+    n = 2_000_000
+    mm = -2 * np.pi / rng.uniform(50., 50e3, n) * rng.choice([-1., 1.], n)
+    kh = 2 * np.pi / rng.uniform(2e3, 2000e3, n)
+    th = rng.uniform(0, 2 * np.pi, n)
+    kk, ll = kh * np.sin(th), kh * np.cos(th)
+    phi = rng.uniform(-1.4, 1.4, n) * rng.choice([0., 1.], n)
+    mm[:1000] *= 1e-9; kk[1000:2000] = 0.0; ll[1000:1500] = 0.0; mm[3000:3100] = 0.0    # degenerate wavenumbers
+    ff = 2 * 7.2921e-5 * np.sin(phi)
+    for bvf in (0.01, 0.02):
+        want = oracle.Oracle(dict(bvf=bvf, phi0=0.0, grid=np.linspace(0, 1, 4), grids=np.array([.1, .2, .3]), dkk=1, dll=1,
+                                  rr_mm_area=0)).lib
+        t = [eng.dev(a) for a in (kk, ll, mm, ff)]
+        out = eng.empty(n)
+        check(lib.msgwam_debug_cg_rr_fast(*[eng.ptr(x) for x in t], bvf ** 2, eng.ptr(out), n, eng.stream))
+        got = out.cpu().numpy()
+        # the oracle's cg_rr1 takes ff directly: (-mm)*(om*om - f2)/om/vk
+        f2 = ff * ff
+        kh2 = kk * kk + ll * ll
+        with np.errstate(all="ignore"):
+            om = np.sqrt((bvf ** 2 * kh2 + f2 * (mm * mm)) / (kh2 + mm * mm))
+            ref = (-mm) * (om * om - f2) / om / (kh2 + mm * mm)
+        same = (got == ref) | (np.isnan(got) & np.isnan(ref))
+        assert same.all(), (bvf, int((~same).sum()), got[~same][:3], ref[~same][:3])

@@ -32,10 +32,11 @@ def main():
             fb = lambda: check(lib.msgwam_column_pass_b(p, rays, ens.n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out), eng.stream))
             ff = lambda: check(lib.msgwam_column_finish(p, g, P(ens.uu), P(ens.vv), P(ens.work), P(uo), P(vo), eng.stream))
             def step(): fa(); fb(); ff()
+            def fused(): check(lib.msgwam_column_step(p, rays, ens.n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out), P(uo), P(vo), eng.stream))
             for _ in range(3): step()
             res = dict(n=n, shuffled=shuffled, pass_a_us=time_it(fa, 10, flush), pass_b_us=time_it(fb, 10, flush),
-                       finish_us=time_it(ff, 10, flush), step_us=time_it(step, 10, flush), step_us_noflush=time_it(step, 10, None))
-            if n: res["ray_steps_per_s"] = n / (res["step_us"] * 1e-6)
+                       finish_us=time_it(ff, 10, flush), step_us=time_it(step, 10, flush), fused_us=time_it(fused, 10, flush), fused_us_noflush=time_it(fused, 10, None))
+            if n: res["ray_steps_per_s"] = n / (res["fused_us"] * 1e-6)
             print(json.dumps(res), flush=True)
             if n == 0 and shuffled: pass
 main()

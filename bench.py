@@ -220,7 +220,9 @@ def run_ours(args, rank, local_rank, world):
     for i in range(11):
         var[i] = keep[i].numpy()
     lprop.set_statics(dkk=keep[11].numpy(), dll=keep[12].numpy(), rr_mm_area=keep[13].numpy())
-    h2d = 10 * n * 8 + (ens.G + 1 + 6 * ens.G) * 8          # dens, phi, rr, drr, kk, ll, mm, dmm, dkk, dll + grid fields
+    # per step: dens, phi, rr, drr, kk, ll, mm, dmm + grid fields (the per-run statics dkk, dll are uploaded by the
+    # first call only, as long as the caller keeps passing the same arrays)
+    h2d = 8 * n * 8 + (ens.G + 1 + 6 * ens.G) * 8
     d2h = 2 * n * 8 + 2 * ens.G * 8                          # rr, mm, uu, vv
     if world == 1:
         def e2e_step():

@@ -198,7 +198,8 @@ int msgwam_compact(int64_t n, const uint8_t *d_keep, int32_t nfields,
  * Copies the step's inputs host->device, runs the column step, copies rr, mm, uu, vv back.
  * All h_* are host pointers (pinned or pageable); d_stage is a device scratch of
  * msgwam_host_stage_doubles(n, G) doubles; d_work as in msgwam_column_step.
- * Synchronises `stream` before returning (the outputs are host memory). */
+ * h_dkk == h_dll == NULL reuses the statics a previous call with the same n left in d_stage (they are
+ * per-run constants, L:722-726).  Synchronises `stream` before returning (the outputs are host memory). */
 int64_t msgwam_host_stage_doubles(int64_t n, int32_t G);
 int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n,
                            const double *const h_state[9], const double *h_dkk, const double *h_dll,

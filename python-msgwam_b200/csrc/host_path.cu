@@ -41,7 +41,8 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
         !d_stage || !d_work)
         return MSGWAM_E_BADARG;
     if (p->G < 3) return MSGWAM_E_GRID_SIZE;
-    if (n > 0 && (!h_dkk || !h_dll || !h_rr_out || !h_mm_out)) return MSGWAM_E_BADARG;
+    if (n > 0 && (!h_rr_out || !h_mm_out)) return MSGWAM_E_BADARG;
+    if ((h_dkk == nullptr) != (h_dll == nullptr)) return MSGWAM_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t np = pad32(n), G = p->G, gp = pad32(G);
     double *d = d_stage;
@@ -63,7 +64,8 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
     } while (0)
     MW_H2D(d_grid, h_grid, G + 1); MW_H2D(d_grids, h_grids, G); MW_H2D(d_rho, h_rhobar, G); MW_H2D(d_pg, h_pg, 2 * G);
     MW_H2D(d_uu, h_uu, G); MW_H2D(d_vv, h_vv, G);
-    MW_H2D(d_phi, h_state[2], n); MW_H2D(d_dkk, h_dkk, n); MW_H2D(d_dll, h_dll, n);
+    MW_H2D(d_phi, h_state[2], n);
+    if (h_dkk) { MW_H2D(d_dkk, h_dkk, n); MW_H2D(d_dll, h_dll, n); }   // NULL: reuse the statics left in d_stage
     int rc = msgwam_derive_statics(d_phi, d_dkk, d_dll, d_ff, d_pkl, n, p->two_rot, stream);
     if (rc) return rc;
     MW_H2D(d_dens, h_state[0], n); MW_H2D(d_rr, h_state[3], n); MW_H2D(d_drr, h_state[4], n); MW_H2D(d_kk, h_state[5], n);

@@ -9,7 +9,7 @@ rows = run([])
 hdr = rows[1]; ia = hdr.index('Source'); ie = hdr.index('Instructions Executed'); isamp = hdr.index('# Samples')
 byop = collections.Counter(); tot = 0
 for r in rows[2:]:
-    if len(r) <= ie: continue
+    if len(r) <= ie or not (r[ie] or '0').isdigit(): continue
     m = re.match(r'(@!?U?P\d+\s+)?([A-Z0-9_.]+)', r[ia].strip())
     op = m.group(2).split('.')[0] if m else r[ia].strip()
     n = int(r[ie] or 0); byop[op] += n; tot += n

@@ -155,18 +155,29 @@ def run_ours(args, rank, local_rank, world):
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     P = eng.ptr
 
+    from msgwam_b200.distributed import PeerExchange
+    exchange = PeerExchange.get(ens.G) if world > 1 else None
+
     def reduce_(t):
-        if world > 1:
+        if world > 1 and exchange is None:
             dist.all_reduce(t)
 
     def pass_a():
         check(lib.msgwam_column_pass_a(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), eng.stream), "pass_a")
 
     def pass_b():
-        check(lib.msgwam_column_pass_b(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out), eng.stream), "pass_b")
+        if exchange is not None:      # chain kernel all-reduces D0|D1 over peer memory, then the sweep
+            check(lib.msgwam_column_pass_b_p2p(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out),
+                                               exchange.next(), eng.stream), "pass_b_p2p")
+        else:
+            check(lib.msgwam_column_pass_b(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out), eng.stream), "pass_b")
 
     def finish():
-        check(lib.msgwam_column_finish(p, g, P(ens.uu), P(ens.vv), P(ens.work), P(uu_out), P(vv_out), eng.stream), "finish")
+        if exchange is not None:
+            check(lib.msgwam_column_finish_p2p(p, g, P(ens.uu), P(ens.vv), P(ens.work), P(uu_out), P(vv_out), exchange.next(),
+                                               eng.stream), "finish_p2p")
+        else:
+            check(lib.msgwam_column_finish(p, g, P(ens.uu), P(ens.vv), P(ens.work), P(uu_out), P(vv_out), eng.stream), "finish")
 
     def step():          # out of place: every timed step does identical work on the same input state
         pass_a(); reduce_(ens.work[:4 * nc]); pass_b(); reduce_(ens.work[4 * nc:6 * nc]); finish()
@@ -277,7 +288,8 @@ def run_ours(args, rank, local_rank, world):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: 1e6 ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000",
                    "rays_per_gpu": n, "grid_levels": ens.G, "dt_s": sc.dt, "l2": "flushed between timed steps (256 MiB write)",
-                   "parallelism": "rays sharded, %d rank(s); all-reduce of the deposited flux twice per step" % world,
+                   "parallelism": "rays sharded, %d rank(s); all-reduce of the deposited flux twice per step (%s)" % (
+                       world, "none needed" if world == 1 else ("fused into the chain/finish kernels over NVLink peer memory" if exchange is not None else "NCCL")),
                    "mode": "M1 coupled (reference RK3 semantics: mean flow inside the RK state), 2 ray sweeps per step"},
         "roofline": {"bound": "hbm", "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak, "traffic": None,
                      "kernel": "column_pass<1> (pass B: stages 1-3 + deposit + store)",

@@ -114,6 +114,29 @@ int msgwam_column_pass_b(const msgwam_params_t *p, const msgwam_rays_t *rays, in
 int msgwam_column_finish(const msgwam_params_t *p, const msgwam_grid_t *grid,
                          const double *d_uu, const double *d_vv, double *d_work,
                          double *d_uu_out, double *d_vv_out, void *stream);
+/* Multi-GPU without a separate collective: the one-CTA chain / finish kernels all-reduce the deposit
+ * themselves with one-shot pushes over NVLink peer memory.  inbox[r] is rank r's inbox buffer
+ * (msgwam_p2p_inbox_doubles(G, world) doubles, zero-initialised once, allocated in symmetric / IPC memory)
+ * as mapped into THIS process; epoch must be identical on all ranks and increase by one per reduction
+ * (pass_b_p2p and finish_p2p each perform one).  A peer that does not answer within ~20 s sets the error
+ * word returned by msgwam_column_error() instead of hanging the GPU. */
+#define MSGWAM_MAX_PEERS 16
+typedef struct msgwam_peers {
+    int32_t world, rank;
+    uint64_t epoch;
+    void *inbox[MSGWAM_MAX_PEERS];
+} msgwam_peers_t;
+int64_t msgwam_p2p_inbox_doubles(int32_t G, int32_t world);
+int msgwam_column_pass_b_p2p(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                             const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                             double *d_work, double *d_rr_out, double *d_mm_out,
+                             const msgwam_peers_t *peers, void *stream);
+int msgwam_column_finish_p2p(const msgwam_params_t *p, const msgwam_grid_t *grid,
+                             const double *d_uu, const double *d_vv, double *d_work,
+                             double *d_uu_out, double *d_vv_out, const msgwam_peers_t *peers, void *stream);
+/* offset (in doubles) inside d_work of the error word set by a timed-out peer exchange (0.0 = ok) */
+int64_t msgwam_column_error_offset(int32_t G);
+
 /* single GPU: two launches -- the mean-flow chain and the finish run as the tails of the sweeps, in the last
  * CTA to retire */
 int msgwam_column_step(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,

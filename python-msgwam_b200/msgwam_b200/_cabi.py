@@ -37,6 +37,14 @@ class Rays(ctypes.Structure):
     _fields_ = [(k, c_void_p) for k in _RAY_FIELDS]
 
 
+MAX_PEERS = 16
+
+
+class Peers(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("epoch", ctypes.c_uint64),
+                ("inbox", c_void_p * MAX_PEERS)]
+
+
 class Grid(ctypes.Structure):
     _fields_ = [(k, c_void_p) for k in ("grid", "grids", "rhobar", "pg")]
 
@@ -56,6 +64,10 @@ SIGNATURES = {
     "msgwam_column_pass_a": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp]),
     "msgwam_column_pass_b": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_column_finish": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "msgwam_p2p_inbox_doubles": (_i64, [_i32, _i32]),
+    "msgwam_column_pass_b_p2p": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Peers), _vp]),
+    "msgwam_column_finish_p2p": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Peers), _vp]),
+    "msgwam_column_error_offset": (_i64, [_i32]),
     "msgwam_column_step": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_debug_cg_rr_fast": (ctypes.c_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _i64, _vp]),
     "msgwam_rhs_rays": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp]),

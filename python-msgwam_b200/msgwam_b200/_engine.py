@@ -128,10 +128,11 @@ class Engine:
 
     # ---- fused column step on device tensors ---------------------------------------------------
     def column_step(self, p: Params, state, dkk, dll, uu, vv, grid_devs, rr_out=None, mm_out=None,
-                    reduce_fn=None):
+                    reduce_fn=None, exchange=None):
         """state: 9 device tensors (reference order).  Returns (rr_new, mm_new, uu_new, vv_new).
 
-        reduce_fn(tensor) -- optional in-place all-reduce of the deposit buffers (multi-GPU)."""
+        Multi-GPU: exchange (distributed.PeerExchange) fuses the all-reduce of the deposit into the chain /
+        finish kernels over peer memory; otherwise reduce_fn(tensor) all-reduces the buffers in place (NCCL)."""
         dens, lam, phi, rr, drr, kk, ll, mm, dmm = state
         n = rr.numel()
         ff, pkl = self.derived_statics(phi, dkk, dll, p.two_rot)
@@ -145,7 +146,13 @@ class Engine:
         mm_out = self.empty(n) if mm_out is None else mm_out
         uu_out, vv_out = self.empty(p.G), self.empty(p.G)
         s = self.stream
-        if reduce_fn is None:
+        if exchange is not None:
+            check(lib.msgwam_column_pass_a(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), s), "msgwam_column_pass_a")
+            check(lib.msgwam_column_pass_b_p2p(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
+                                               self.ptr(mm_out), exchange.next(), s), "msgwam_column_pass_b_p2p")
+            check(lib.msgwam_column_finish_p2p(p, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(uu_out),
+                                               self.ptr(vv_out), exchange.next(), s), "msgwam_column_finish_p2p")
+        elif reduce_fn is None:
             check(lib.msgwam_column_step(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
                                          self.ptr(mm_out), self.ptr(uu_out), self.ptr(vv_out), s), "msgwam_column_step")
         else:

@@ -10,7 +10,59 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import _cabi
 from ._engine import Engine
+
+
+class PeerExchange:
+    """Symmetric-memory inboxes for the all-reduce that is fused into the chain / finish kernels
+    (csrc/column_step.cu: p2p_allreduce).  One instance per (G, process group); `next()` hands out the
+    msgwam_peers_t of the next reduction -- the epoch sequence is identical on all ranks because every rank
+    runs the same sequence of steps."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, G):
+        """The exchange for grids of G levels, or None (single rank, MSGWAM_NCCL_ALLREDUCE=1, or symmetric
+        memory unavailable -- then the caller all-reduces with NCCL)."""
+        import os
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+            return None
+        if os.environ.get("MSGWAM_NCCL_ALLREDUCE", "0") == "1" or dist.get_world_size() > _cabi.MAX_PEERS:
+            return None
+        if G not in cls._cache:
+            try:
+                cls._cache[G] = cls(G)
+            except Exception as exc:                      # no P2P / symmetric memory on this system
+                import warnings
+                warnings.warn("msgwam_b200: peer-memory all-reduce unavailable (%s); using NCCL" % (exc,))
+                cls._cache[G] = None
+        return cls._cache[G]
+
+    def __init__(self, G):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        eng = Engine.get()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        n = int(_cabi.lib.msgwam_p2p_inbox_doubles(G, self.world))
+        self.inbox = symm_mem.empty(n, dtype=torch.float64, device=eng.device)
+        self.inbox.zero_()
+        self.handle = symm_mem.rendezvous(self.inbox, dist.group.WORLD.group_name)
+        torch.cuda.synchronize()
+        self.handle.barrier()                             # every inbox is zeroed before anyone pushes
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.epoch = 0
+
+    def next(self):
+        self.epoch += 1
+        pe = _cabi.Peers()
+        pe.world, pe.rank, pe.epoch = self.world, self.rank, self.epoch
+        for r, ptr in enumerate(self.ptrs):
+            pe.inbox[r] = ptr
+        return pe
 
 
 def all_reduce_sum(t):
@@ -19,11 +71,16 @@ def all_reduce_sum(t):
         dist.all_reduce(t)
 
 
+_stage = {}          # (n, device) -> staging slab for the sharded host path
+
+
 def rk3_host_sharded(lprop, dt, var):
     """lprop.RK3 for this rank's slice of the rays, given as HOST numpy arrays (column mode only).
 
-    Same contract as lprop.RK3: returns a fresh 11-slot object array of numpy arrays; uu, vv are the
-    globally coupled mean flow (identical on every rank).
+    Same contract as lprop.RK3: returns an 11-slot object array of numpy arrays; uu, vv are the globally
+    coupled mean flow (identical on every rank).  The step's inputs go host->device with asynchronous copies
+    on the compute stream (page-locked arrays are copied without staging), the two all-reduces of the
+    deposit sit between the sweeps, and rr, mm, uu, vv come back into page-locked arrays.
     """
     eng = Engine.get()
     torch = eng.torch
@@ -31,17 +88,39 @@ def rk3_host_sharded(lprop, dt, var):
     if p.hprop or p.saturate_online:
         raise NotImplementedError("sharded host path covers the column mode (HPROP off, saturate_online off)")
     n = int(np.size(var[3]))
-    up = lambda a, m: torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (m,)))).to(eng.device, non_blocking=True)
-    state = [up(a, n) if i != 1 else None for i, a in enumerate(var[:9])]       # lam is not needed on the device
-    state[1] = state[2]
-    dkk, dll = up(lprop.statics['dkk'], n), up(lprop.statics['dll'], n)
-    uu, vv = up(var[9], p.G), up(var[10], p.G)
+    host = [lprop._host_f64(a, n) for a in var[:9]]
+    dkk, dll = lprop._host_f64(lprop.statics['dkk'], n), lprop._host_f64(lprop.statics['dll'], n)
+    key = (n, eng.device)
+    st = _stage.get(key)
+    if st is None:
+        _stage.clear()
+        st = dict(slab=eng.empty(10, max(n, 1)), statics=None)
+        _stage[key] = st
+    slab = st["slab"]
+
+    def up(row, a):
+        t = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
+        slab[row, :n].copy_(t, non_blocking=True)
+        return slab[row, :n]
+    # dens, phi, rr, drr, kk, ll, mm, dmm (lam is not needed on the device)
+    dev = {i: up(k, host[i]) for k, i in enumerate((0, 2, 3, 4, 5, 6, 7, 8))}
+    skey = (id(lprop.statics['dkk']), id(lprop.statics['dll']), dkk.ctypes.data, dll.ctypes.data)
+    if st["statics"] != skey:
+        up(8, dkk); up(9, dll)
+        st["statics"] = skey
+    state = [dev[0], dev[2], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8]]
+    uu = torch.from_numpy(np.ascontiguousarray(var[9], dtype=np.float64)).to(eng.device, non_blocking=True)
+    vv = torch.from_numpy(np.ascontiguousarray(var[10], dtype=np.float64)).to(eng.device, non_blocking=True)
     gd = lprop._grid_devs(eng)
-    rr_new, mm_new, uu_new, vv_new = eng.column_step(p, state, dkk, dll, uu, vv, gd, reduce_fn=all_reduce_sum)
-    host = lambda t: t.cpu().numpy()
-    cp = lambda a: np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,)))
-    return lprop._pack11([cp(var[0]), cp(var[1]), cp(var[2]), host(rr_new), cp(var[4]), cp(var[5]), cp(var[6]),
-                          host(mm_new), cp(var[8]), host(uu_new), host(vv_new)])
+    rr_new, mm_new, uu_new, vv_new = eng.column_step(p, state, slab[8, :n], slab[9, :n], uu, vv, gd, reduce_fn=all_reduce_sum,
+                                                     exchange=PeerExchange.get(p.G))
+    outs = [lprop._pinned_empty(eng, n), lprop._pinned_empty(eng, n), lprop._pinned_empty(eng, p.G), lprop._pinned_empty(eng, p.G)]
+    for o, t in zip(outs, (rr_new, mm_new, uu_new, vv_new)):
+        torch.from_numpy(o).copy_(t, non_blocking=True)
+    torch.cuda.current_stream(eng.device).synchronize()
+    u = lprop._unchanged
+    return lprop._pack11([u(host[0]), u(host[1]), u(host[2]), outs[0], u(host[4]), u(host[5]), u(host[6]), outs[1],
+                          u(host[8]), outs[2], outs[3]])
 
 
 def shard_range(n: int, rank: int, world: int):

@@ -57,6 +57,10 @@ class RayEnsemble:
         self._uu2, self._vv2 = eng.empty(self.G), eng.empty(self.G)
         self.work = eng.zeros(int(lib.msgwam_column_work_doubles(self.G)))
         self.dist = _dist() if distributed is None else (distributed or None)
+        self.exchange = None
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            from .distributed import PeerExchange
+            self.exchange = PeerExchange.get(self.G)
         self._derive()
 
     @classmethod
@@ -105,12 +109,19 @@ class RayEnsemble:
                 rr, mm = self.field("rr"), self.field("mm")
                 check(lib.msgwam_column_pass_a(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work), s),
                       "msgwam_column_pass_a")
-                self._reduce(self.work[:4 * nc])
-                check(lib.msgwam_column_pass_b(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
-                                               eng.ptr(rr), eng.ptr(mm), s), "msgwam_column_pass_b")
-                self._reduce(self.work[4 * nc:6 * nc])
-                check(lib.msgwam_column_finish(p, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
-                                               eng.ptr(self._uu2), eng.ptr(self._vv2), s), "msgwam_column_finish")
+                if self.exchange is not None:       # all-reduce fused into the chain / finish kernels (peer memory)
+                    check(lib.msgwam_column_pass_b_p2p(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
+                                                       eng.ptr(rr), eng.ptr(mm), self.exchange.next(), s), "msgwam_column_pass_b_p2p")
+                    check(lib.msgwam_column_finish_p2p(p, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
+                                                       eng.ptr(self._uu2), eng.ptr(self._vv2), self.exchange.next(), s),
+                          "msgwam_column_finish_p2p")
+                else:
+                    self._reduce(self.work[:4 * nc])
+                    check(lib.msgwam_column_pass_b(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
+                                                   eng.ptr(rr), eng.ptr(mm), s), "msgwam_column_pass_b")
+                    self._reduce(self.work[4 * nc:6 * nc])
+                    check(lib.msgwam_column_finish(p, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
+                                                   eng.ptr(self._uu2), eng.ptr(self._vv2), s), "msgwam_column_finish")
                 eng.launches += 3
                 self.uu, self._uu2 = self._uu2, self.uu
                 self.vv, self._vv2 = self._vv2, self.vv
@@ -148,6 +159,12 @@ class RayEnsemble:
         self._slab, self._slab2 = self._slab2, self._slab
         self.n = int(count.item())
         return self.n
+
+    def check_errors(self):
+        """Raise if a peer exchange timed out (synchronises the stream)."""
+        off = int(lib.msgwam_column_error_offset(self.G))
+        if float(self.work[off].item()) != 0.0:
+            raise _cabi.MsgwamError("peer-memory all-reduce timed out: a rank did not deliver its deposit")
 
     # ---- export -----------------------------------------------------------------------------------
     def to_var(self):

@@ -37,6 +37,9 @@ UNIT = "ray-steps/s"
 A_STEP = 96.0      # algorithmic B/ray-step, SURVEY.md 8(d): 10 fp64 fields read once + rr, mm written once
 A_PASS_A = 72.0    # pass A: 9 fields read (dens, ff, rr, drr, kk, ll, mm, dmm, dkk*dll), nothing written
 A_PASS_B = 88.0    # pass B: the same 9 fields read + rr, mm written
+# dram__bytes_read.sum + dram__bytes_write.sum of pass B from the committed `ncu --set full` capture at 1e6 rays
+# (profiles/r01_column_pass_ncu_full_summary.json: 72.17 MB + 3.23 MB; the 16 MB of results mostly stay in L2)
+NCU_TRAFFIC_PASS_B_PER_RAY = 75.4
 
 
 def measured_peaks():
@@ -291,7 +294,8 @@ def run_ours(args, rank, local_rank, world):
                    "parallelism": "rays sharded, %d rank(s); all-reduce of the deposited flux twice per step (%s)" % (
                        world, "none needed" if world == 1 else ("fused into the chain/finish kernels over NVLink peer memory" if exchange is not None else "NCCL")),
                    "mode": "M1 coupled (reference RK3 semantics: mean flow inside the RK state), 2 ray sweeps per step"},
-        "roofline": {"bound": "hbm", "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak,
+                     "traffic": NCU_TRAFFIC_PASS_B_PER_RAY * n, "traffic_source": "ncu --set full, profiles/r01_column_pass_ncu_full_summary.json (75.4 B/ray at 1e6 rays)",
                      "kernel": "column_pass<1> (pass B: stages 1-3 + deposit + store)",
                      "algorithmic_bytes_per_ray": A_PASS_B, "kernel_ms": t_b * 1e3, "peak_source": peak_src,
                      "other_kernels": {"column_pass<0>": {"ms": t_a * 1e3, "achieved_gbs": A_PASS_A * n / t_a / 1e9,

@@ -178,3 +178,35 @@ def column_ensemble(n: int, seed: int = 1234, ngrid: int = 1001, sheared: bool =
         stat = [a[perm] for a in stat]
     name = "column_%s%s_n%d" % ("sheared" if sheared else "constN", "_shuffled" if shuffled else "", n)
     return Scenario(name, 120., state, uu, vv, stat[0], stat[1], stat[2], grid, grids, rhobar, pg, model, hprop=False)
+
+
+def critical_level_ensemble(n: int, seed: int = 4321, ngrid: int = 1001) -> Scenario:
+    """BASELINE.json configs[4] (constant-N variant): a jet U(z) = 20 m/s * exp(-(z - 30 km)^2 / (2 (5 km)^2)).
+    Rays whose horizontal wavenumber is parallel to the jet are refracted towards a critical level
+    (|m| grows without bound, c_g -> 0: they pile up below the jet); antiparallel rays run out of the top.
+    Half of the rays have either sign of k; l = 0.  Ray deletion (RayEnsemble.compact) removes both kinds."""
+    rng = np.random.default_rng(seed)
+    NN = 0.01
+    grid = np.linspace(0, 100e3, ngrid)
+    grids = .5 * (grid[:-1] + grid[1:])
+    edges = np.linspace(0, 25e3, n + 1)
+    rr = .5 * (edges[:-1] + edges[1:])
+    drr = rng.uniform(50., 300., n)
+    mm = -2 * np.pi / rng.uniform(1e3, 5e3, n)
+    kk = 2 * np.pi / rng.uniform(20e3, 100e3, n) * rng.choice([-1., 1.], n)
+    ll = np.zeros(n)
+    dmm = 1e-4 * np.abs(mm)
+    dkk = np.full(n, 1e-4)
+    dll = np.full(n, 1e-4)
+    area = dmm * drr
+    model = dict(bvf=NN, phi0=0.0, kappa=1., saturate_online=False)
+    rhobar = _hydrostatic_rhobar(grids)
+    uu = 20. * np.exp(-(grids - 30e3) ** 2 / 2 / 5e3 ** 2)
+    vv = np.zeros(grids.shape)
+    omh = np.sqrt(NN ** 2 * (kk ** 2 + ll ** 2) / (kk ** 2 + ll ** 2 + mm ** 2))
+    rho_ray = np.interp(rr, grids, rhobar)
+    per_cell = max(1.0, n * float(np.mean(drr)) / 25e3)
+    dens = 0.1 ** 2 * rho_ray / 2 * omh / mm ** 2 / omh ** 2 * NN ** 2 / dkk / dll / dmm / per_cell
+    pg = _geostrophic_pg(rhobar, 0.0, uu, vv)
+    return Scenario("critical_level_n%d" % n, 120., [dens, np.zeros(n), np.zeros(n), rr, drr, kk, ll, mm, dmm], uu, vv,
+                    dkk, dll, area, grid, grids, rhobar, pg, model, hprop=False)

@@ -95,3 +95,46 @@ def test_compaction_all_and_none():
     assert ens.compact(m_crit=float("inf")) == int(_keep_mask(sc, sc.state[3], sc.state[4], sc.state[7], np.inf).sum())
     assert ens.compact(m_crit=0.0) == 0
     assert ens.compact(m_crit=1.0) == 0
+
+
+def test_critical_level_run_with_periodic_deletion():
+    """BASELINE configs[4] in miniature: jet, rays refracted towards critical levels / out of the top, deletion
+    every 10 steps.  Oracle = reference RK3 on arrays (and statics) filtered by the same predicate."""
+    from msgwam_b200.ensemble import RayEnsemble, STATE
+    sc = scenarios.critical_level_ensemble(30011, ngrid=401)
+    m_crit = 6.3e-3            # just above the initial maximum of |m| (2 pi / 1 km): refracted rays cross it within a few steps
+    ens = RayEnsemble.from_scenario(sc)
+    state = [a.copy() for a in sc.state]
+    stat = [sc.dkk.copy(), sc.dll.copy(), sc.rr_mm_area.copy()]
+    uu, vv = sc.uu.copy(), sc.vv.copy()
+    deleted = 0
+    for cycle in range(4):
+        cfg = sc.oracle_cfg(); cfg.update(dkk=stat[0], dll=stat[1], rr_mm_area=stat[2])
+        orc = oracle.Oracle(cfg)
+        var = np.empty(11, dtype=object)
+        for i in range(9):
+            var[i] = state[i]
+        var[9], var[10] = uu, vv
+        start = [a.copy() for a in var[:9]]
+        for _ in range(10):
+            var = orc.RK3(sc.dt, var)
+        ens.step(sc.dt, 10)
+        got = ens.to_var()
+        for i, nm in enumerate(FIELDS):
+            if nm in ("uu", "vv"):
+                assert field_rel(got[i], var[i]) <= 1e-11, (cycle, nm, field_rel(got[i], var[i]))
+            else:
+                scale = np.maximum(np.abs(var[i]), np.abs(var[i] - start[i]))
+                diff = np.abs(got[i] - var[i])
+                err = float(np.max(np.where(diff == 0, 0.0, diff / np.where(scale == 0, 1.0, scale))))
+                assert err <= 1e-11, (cycle, nm, err)
+        keep = _keep_mask(sc, var[3], var[4], var[7], m_crit)
+        survivors = ens.compact(m_crit=m_crit)
+        assert survivors == int(keep.sum())
+        deleted += int((~keep).sum())
+        state = [np.asarray(var[i])[keep] for i in range(9)]
+        stat = [a[keep] for a in stat]
+        uu, vv = np.asarray(var[9]), np.asarray(var[10])
+        for i, nm in enumerate(STATE):
+            assert np.array_equal(ens.field(nm).cpu().numpy(), np.asarray(got[i])[keep]), (cycle, nm)
+    assert deleted > 0 and ens.n > 0

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MSGWAM_ABI_VERSION 1
+#define MSGWAM_ABI_VERSION 2
 
 #define MSGWAM_E_BADARG      (-1)   /* null pointer / negative size / inconsistent arguments   */
 #define MSGWAM_E_GRID_SIZE   (-2)   /* G too small (< 3) or too large for the fused column kernels */
@@ -74,6 +74,10 @@ typedef struct msgwam_grid {
     const double *grids;    /* (G,)   staggered grid             lprop.grids             */
     const double *rhobar;   /* (G,)                              lprop.rhobar            */
     const double *pg;       /* (2,G)                             lprop.pressure_gradient */
+    const double *bvf;      /* (G,) or NULL.  EXTENSION, not in the reference: buoyancy
+                               frequency N on `grids`; N^2(z) = np.interp(z, grids, bvf)**2 replaces the scalar
+                               params.n2 at the position argument of cg_rr / cg_lambda / cg_phi, and dm_dt gains
+                               -N N'(k^2+l^2)/om/|k|^2.  Only the general (stage-by-stage) entry points use it. */
 } msgwam_grid_t;
 
 int         msgwam_abi_version(void);
@@ -172,6 +176,7 @@ int msgwam_rk_update(int32_t stage, double dt, const double *d_tend, double *d_q
 /* ---- deposition  (replaces wave_projection L:92-221, var = 0..4, any uniform grid) ----------
  * out sizes: var 0 -> 2*(ng-1); 1,2 -> ng-1; 3 -> ng; 4 -> 2*ng doubles, zeroed by the call.
  * dz = np.diff(grid[:2])[0] of the grid passed (L:123) and inv_dz = 1.0/dz, derived by the host. */
+/* d_bvf/d_bvf_grids: NULL, or the N(z) extension's profile and its abscissa (grids) -- see msgwam_grid_t.bvf */
 int msgwam_wave_projection(int32_t var, const msgwam_params_t *p, int64_t n,
                            const double *d_dens, const double *d_phi,
                            const double *d_rr_low, const double *d_rr_up,
@@ -179,6 +184,7 @@ int msgwam_wave_projection(int32_t var, const msgwam_params_t *p, int64_t n,
                            const double *d_mm_low, const double *d_mm_up,
                            const double *d_dkk, const double *d_dll, const double *d_dmm,
                            const double *d_grid, int32_t ng, double dz, double inv_dz,
+                           const double *d_bvf, const double *d_bvf_grids,
                            double *d_out, void *stream);
 
 /* ---- saturation  (replaces saturation L:561-615; direct = 0 tendency, 1 clamp) --------------*/
@@ -188,7 +194,8 @@ int msgwam_saturation(const msgwam_params_t *p, int64_t n, int32_t direct,
                       const double *d_kk, const double *d_ll,
                       const double *d_mm, const double *d_mm_st,
                       const double *d_dkk, const double *d_dll, const double *d_area,
-                      const double *d_grids, const double *d_rhobar, double *d_out, void *stream);
+                      const double *d_grids, const double *d_rhobar, const double *d_bvf /* NULL or N on grids */,
+                      double *d_out, void *stream);
 
 /* ---- point functions (replace omega L:369, cg_rr L:434, cg_lambda L:386, cg_phi L:410,
  *      dk_dt L:451, dl_dt L:474, dm_dt L:502, gradients L:328) ------------------------------
@@ -202,7 +209,8 @@ enum {
 };
 int msgwam_pointwise(int32_t op, const msgwam_params_t *p, int64_t n,
                      const double *d_kk, const double *d_ll, const double *d_mm,
-                     const double *d_phi, const double *d_rr, double f, double f2,
+                     const double *d_phi, const double *d_rr /* also read by omega / cg_rr when grid->bvf is set */,
+                     double f, double f2,
                      const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
                      double *d_out, void *stream);
 

@@ -33,6 +33,7 @@ class _Params(ctypes.Structure):
         ("k2half", ctypes.c_double), ("dz_grid", ctypes.c_double), ("dz_grids", ctypes.c_double),
         ("ngrid", ctypes.c_int32), ("hprop", ctypes.c_int32), ("saturate_online", ctypes.c_int32),
         ("nthreads", ctypes.c_int32),
+        ("bvf_prof", ctypes.c_void_p), ("bvf_grids", ctypes.c_void_p),     # extension: N(z) profile on grids
     ]
 
 
@@ -89,6 +90,14 @@ class Oracle:
         kappa = cfg.get("kappa", 1.0)
         f0 = 2 * ROT_EARTH * np.sin(phi0)                  # L:535, 589 (numpy scalar)
         p = _Params()
+        # extension (not in the reference): bvf may be an array of N on `grids`
+        self.bvf_prof = None
+        if np.ndim(bvf) > 0:
+            self.bvf_prof = np.ascontiguousarray(bvf, dtype=np.float64)
+            assert self.bvf_prof.shape == (G,), "bvf profile must live on grids"
+            p.bvf_prof = self.bvf_prof.ctypes.data
+            p.bvf_grids = grids.ctypes.data
+            bvf = float("nan")                             # the scalar must never be used then
         p.n2 = bvf ** 2                                    # L:383
         p.two_rot = 2 * ROT_EARTH                          # L:382
         p.rad_earth = RAD_EARTH
@@ -117,22 +126,31 @@ class Oracle:
         self.lib.orc_interp(xc, ctypes.c_long(x.size), xpc, fpc, ctypes.c_long(xp.size), out.ctypes.data_as(_dp))
         return out
 
-    def omega(self, kk, ll, mm, phi):
+    def _rr(self, rr, n):
+        """Position argument: only the N(z) extension looks at it."""
+        if self.bvf_prof is None or rr is None:
+            assert self.bvf_prof is None, "a bvf profile needs the position argument"
+            return None, None
+        return _c(np.broadcast_to(np.asarray(rr, dtype=np.float64), (n,)))
+
+    def omega(self, kk, ll, mm, phi, rr=None):
         kk, a = _c(kk); ll, b = _c(ll); mm, c = _c(mm)
         out = np.empty_like(kk)
+        keep, r = self._rr(rr, kk.size)
         if np.ndim(phi) == 0:
             f = 2 * ROT_EARTH * np.sin(phi)
-            self.lib.orc_omega_scalar_phi(ctypes.c_long(kk.size), a, b, c, ctypes.c_double(float(f ** 2)),
+            self.lib.orc_omega_scalar_phi(ctypes.c_long(kk.size), a, b, c, ctypes.c_double(float(f ** 2)), r,
                                           ctypes.byref(self.p), out.ctypes.data_as(_dp))
         else:
             phi, d = _c(phi)
-            self.lib.orc_omega(ctypes.c_long(kk.size), a, b, c, d, ctypes.byref(self.p), out.ctypes.data_as(_dp))
+            self.lib.orc_omega(ctypes.c_long(kk.size), a, b, c, d, r, ctypes.byref(self.p), out.ctypes.data_as(_dp))
         return out
 
     def cg_rr(self, kk, ll, mm, lam, phi, rr):
         kk, a = _c(kk); ll, b = _c(ll); mm, c = _c(mm); phi, d = _c(phi)
         out = np.empty_like(kk)
-        self.lib.orc_cg_rr(ctypes.c_long(kk.size), a, b, c, d, ctypes.byref(self.p), out.ctypes.data_as(_dp))
+        keep, r = self._rr(rr, kk.size)
+        self.lib.orc_cg_rr(ctypes.c_long(kk.size), a, b, c, d, r, ctypes.byref(self.p), out.ctypes.data_as(_dp))
         return out
 
     def wave_projection(self, dens, lam, phi, rr_low, rr_up, kk, ll, mm_low, mm_up, dkk, dll, dmm, grid, var=0):

@@ -44,6 +44,12 @@ typedef struct {
     int32_t hprop;      /* HPROP_GLOBAL                                 L:5       */
     int32_t saturate_online; /* model_config['saturate_online']         L:633     */
     int32_t nthreads;   /* 1 = reference order; >1 = OpenMP timing mode           */
+    /* EXTENSION (not in the reference, parity unpinned -- DESIGN.md section 9): height-dependent buoyancy
+       frequency.  bvf_prof = N on the staggered grid bvf_grids (ngrid-1 points) or NULL for the reference's
+       scalar.  N(z) = np.interp(z, grids, bvf), N^2(z) = N(z)**2 wherever the reference uses bvf**2, evaluated
+       at the position argument the reference already passes to cg_rr / cg_lambda / cg_phi. */
+    const double *bvf_prof;
+    const double *bvf_grids;
 } orc_params;
 
 #define INVALID_CELL (-99999)
@@ -83,6 +89,14 @@ void orc_interp(const double *x, long n, const double *xp, const double *fp, lon
     for (long i = 0; i < n; ++i) out[i] = interp1(x[i], xp, fp, m);
 }
 
+/* N^2 at height z: the reference's scalar, or (extension) the square of the interpolated profile */
+static inline double n2_at(const orc_params *P, double z)
+{
+    if (!P->bvf_prof) return P->n2;
+    const double nn = interp1(z, P->bvf_grids, P->bvf_prof, P->ngrid - 1);
+    return nn * nn;
+}
+
 /* ------------------------------------------------------------------------ */
 /* omega(kk, ll, mm, phi)  L:369-383; f and f**2 supplied by the caller so    */
 /* both the array-phi (ff*ff) and the scalar-phi0 (pow) forms are covered.    */
@@ -103,25 +117,26 @@ static inline double cg_rr1(double kk, double ll, double mm, double ff, double n
 }
 
 void orc_omega(long n, const double *kk, const double *ll, const double *mm, const double *phi,
-               const orc_params *P, double *out)
+               const double *rr /* extension only, may be NULL */, const orc_params *P, double *out)
 {
     for (long i = 0; i < n; ++i) {
         const double ff = P->two_rot * sin(phi[i]);
-        out[i] = omega1(kk[i], ll[i], mm[i], ff * ff, P->n2);
+        out[i] = omega1(kk[i], ll[i], mm[i], ff * ff, rr ? n2_at(P, rr[i]) : P->n2);
     }
 }
 
 /* omega with a scalar latitude: f**2 is a numpy-scalar power computed by the caller (L:597) */
 void orc_omega_scalar_phi(long n, const double *kk, const double *ll, const double *mm, double f2,
-                          const orc_params *P, double *out)
+                          const double *rr /* extension only, may be NULL */, const orc_params *P, double *out)
 {
-    for (long i = 0; i < n; ++i) out[i] = omega1(kk[i], ll[i], mm[i], f2, P->n2);
+    for (long i = 0; i < n; ++i) out[i] = omega1(kk[i], ll[i], mm[i], f2, rr ? n2_at(P, rr[i]) : P->n2);
 }
 
 void orc_cg_rr(long n, const double *kk, const double *ll, const double *mm, const double *phi,
-               const orc_params *P, double *out)
+               const double *rr /* extension only, may be NULL */, const orc_params *P, double *out)
 {
-    for (long i = 0; i < n; ++i) out[i] = cg_rr1(kk[i], ll[i], mm[i], P->two_rot * sin(phi[i]), P->n2);
+    for (long i = 0; i < n; ++i)
+        out[i] = cg_rr1(kk[i], ll[i], mm[i], P->two_rot * sin(phi[i]), rr ? n2_at(P, rr[i]) : P->n2);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -165,7 +180,8 @@ void orc_wave_projection(int var, long n,
             cell_range(rr_low[i], rr_up[i], dz, nzmax, &nlow, &nup);
             if (nlow == INVALID_CELL) continue;
             const double psv = fabs(dkk[i] * dll[i] * dmm[i]);
-            const double cgr = cg_rr1(kk[i], ll[i], .5 * (mm_low[i] + mm_up[i]), P->two_rot * sin(phi[i]), P->n2);
+            const double cgr = cg_rr1(kk[i], ll[i], .5 * (mm_low[i] + mm_up[i]), P->two_rot * sin(phi[i]),
+                                      n2_at(P, .5 * (rr_low[i] + rr_up[i])));
             for (long nb = 1; nb < ng - 1; ++nb) {
                 if (nlow < nb && nup > nb) {
                     if (var == 3) out[nb] += (cgr * dens[i]) * psv;
@@ -185,7 +201,7 @@ void orc_wave_projection(int var, long n,
         if (var == 2) v0 = dens[i];             /* L:184 */
         else {
             const double cgr = cg_rr1(kk[i], ll[i], .5 * (mm_low[i] + mm_up[i]),
-                                      P->two_rot * sin(phi[i]), P->n2);     /* L:139-144 */
+                                      P->two_rot * sin(phi[i]), n2_at(P, .5 * (rr_low[i] + rr_up[i])));     /* L:139-144 */
             if (var == 0) { v0 = cgr * kk[i] * dens[i]; v1 = cgr * ll[i] * dens[i]; }   /* L:148-149 */
             else v0 = cgr * dens[i];            /* L:167 */
         }
@@ -215,9 +231,9 @@ void orc_saturation(double dt, long n, const double *dens, const double *rr_c, c
         const double mm_final = mm_c[i] + mm_c_st[i] * dt;
         const double dmm_final = rr_mm_area[i] / drr_final;
         const double rho = interp1(rr_final, grids, rhobar, G);
-        const double omh = omega1(kk[i], ll[i], mm_c[i], P->f0sq, P->n2);
+        const double omh = omega1(kk[i], ll[i], mm_c[i], P->f0sq, n2_at(P, rr_c[i]));   /* ext: N at rr_center */
         const double psv = dkk[i] * dll[i] * dmm_final;
-        const double maxd = P->k2half * rho * omh * P->n2 / (mm_final * mm_final) / (omh * omh - P->f0sq);
+        const double maxd = P->k2half * rho * omh * n2_at(P, rr_final) / (mm_final * mm_final) / (omh * omh - P->f0sq);  /* ext: N at rr_final */
         const int hit = maxd < dens[i] * psv;
         if (direct) out[i] = hit ? maxd : dens[i];
         else out[i] = hit ? (maxd - dens[i]) / dt : 0.0;
@@ -243,7 +259,7 @@ static void deposit_var0(long i0, long i1, const ray_in *s, const double *dkk, c
         cell_range(rl, ru, dz, nzmax, &nlow, &nup);
         if (nlow == INVALID_CELL) continue;
         const double psv = fabs(dkk[i] * dll[i] * s->dmm[i]);
-        const double cgr = cg_rr1(s->kk[i], s->ll[i], .5 * (ml + mu), P->two_rot * sin(s->phi[i]), P->n2);
+        const double cgr = cg_rr1(s->kk[i], s->ll[i], .5 * (ml + mu), P->two_rot * sin(s->phi[i]), n2_at(P, .5 * (rl + ru)));
         const double v0 = cgr * s->kk[i] * s->dens[i], v1 = cgr * s->ll[i] * s->dens[i];
         for (long c = nlow; c < nup; ++c) {
             const double zmin = (grids[c] > rl) ? grids[c] : rl;
@@ -263,12 +279,13 @@ void orc_rhs_default(double dt, long n, const double *const state[9], const doub
     const long ng = P->ngrid, G = ng - 1, nc = G - 1;
     const ray_in s = { state[0], state[1], state[2], state[3], state[4], state[5], state[6], state[7], state[8] };
     const double *dkk = statics[0], *dll = statics[1], *area = statics[2];
-    const double dzg = P->dz_grid, R = P->rad_earth, n2 = P->n2;
+    const double dzg = P->dz_grid, R = P->rad_earth;
 
     /* gradients(): L:349-353; tables on grid[1:-1] (G-1 points) */
-    double *dudz = (double *)malloc(sizeof(double) * 2 * (size_t)(nc > 0 ? nc : 1));
-    double *dvdz = dudz + nc;
+    double *dudz = (double *)malloc(sizeof(double) * 3 * (size_t)(nc > 0 ? nc : 1));
+    double *dvdz = dudz + nc, *dndz = dvdz + nc;
     for (long j = 0; j < nc; ++j) { dudz[j] = (uu[j + 1] - uu[j]) / dzg; dvdz[j] = (vv[j + 1] - vv[j]) / dzg; }
+    if (P->bvf_prof) for (long j = 0; j < nc; ++j) dndz[j] = (P->bvf_prof[j + 1] - P->bvf_prof[j]) / dzg;   /* ext */
     const double *xg = grid + 1;
 
     #pragma omp parallel for schedule(static) if (P->nthreads > 1) num_threads(P->nthreads > 1 ? P->nthreads : 1)
@@ -278,9 +295,16 @@ void orc_rhs_default(double dt, long n, const double *const state[9], const doub
         const double ff = P->two_rot * sphi;
         const double f2 = ff * ff;
         const double vk = kk * kk + ll * ll + mm * mm;
+        const double n2 = n2_at(P, rr);                               /* ext: N^2 at the ray centre */
         const double om = omega1(kk, ll, mm, f2, n2);
-        const double cgr = (-mm) * (om * om - f2) / om / vk;          /* cg_rr, L:448; up == down (L:635-636) */
-        const double cgr_up = cgr, cgr_down = cgr;
+        double cgr_up, cgr_down;                                      /* L:635-636 */
+        if (P->bvf_prof) {
+            cgr_up = cg_rr1(kk, ll, mm, ff, n2_at(P, rr + .5 * s.drr[i]));
+            cgr_down = cg_rr1(kk, ll, mm, ff, n2_at(P, rr - .5 * s.drr[i]));
+        } else {
+            cgr_up = cgr_down = (-mm) * (om * om - f2) / om / vk;     /* cg_rr ignores rr: up == down */
+        }
+        const double cgr = P->bvf_prof ? cg_rr1(kk, ll, mm, ff, n2) : cgr_up;   /* cg_rr at the centre (dk_dt, dl_dt) */
         const double du_ray = interp1(rr, xg, dudz, nc);              /* L:355 */
         const double dv_ray = interp1(rr, xg, dvdz, nc);              /* L:356 */
         double cgl, cgp;                                              /* cg_lambda, cg_phi L:386-431 */
@@ -307,7 +331,11 @@ void orc_rhs_default(double dt, long n, const double *const state[9], const doub
             tend[6][i] = -(ll * cgr + kk * tphi * cgl + mm * mm / 2 / om / vk * df2) / rad - g_phi;   /* L:494-497 */
         } else { tend[5][i] = 0.0; tend[6][i] = 0.0; }
         const double g_rr = kk * du_ray + ll * dv_ray;                /* L:517 */
-        const double dmm_st = (kk * cgl + ll * cgp) / rad - g_rr;     /* L:519-520 */
+        double dmm_st = (kk * cgl + ll * cgp) / rad - g_rr;           /* L:519-520 */
+        if (P->bvf_prof) {                                            /* ext: - N N' (k^2 + l^2) / om / |k|^2 */
+            const double nr = interp1(rr, grids, P->bvf_prof, G), dnr = interp1(rr, xg, dndz, nc);
+            dmm_st = dmm_st - nr * dnr * (kk * kk + ll * ll) / om / vk;
+        }
         tend[7][i] = dmm_st;
         tend[8][i] = s.dmm[i] / s.drr[i] * ddrr_st;                   /* L:645 */
         {   /* saturation(dt, dens, rr, drr_st, drr, ddrr_st, kk, ll, mm, dmm_st)  L:647-651 */
@@ -318,7 +346,7 @@ void orc_rhs_default(double dt, long n, const double *const state[9], const doub
             const double rho = interp1(rr_final, grids, rhobar, G);
             const double omh = omega1(kk, ll, mm, P->f0sq, n2);
             const double psv = dkk[i] * dll[i] * dmm_final;
-            const double maxd = P->k2half * rho * omh * n2 / (mm_final * mm_final) / (omh * omh - P->f0sq);
+            const double maxd = P->k2half * rho * omh * n2_at(P, rr_final) / (mm_final * mm_final) / (omh * omh - P->f0sq);
             const double st = (maxd < s.dens[i] * psv) ? (maxd - s.dens[i]) / dt : 0.0;
             tend[0][i] = (double)(P->saturate_online ? 1 : 0) * st;  /* bool * ndarray */
         }

@@ -40,7 +40,7 @@ struct RhsArgs {
     msgwam_params_t p;
     msgwam_rays_t r;
     int64_t n;
-    const double *grid, *grids, *rhobar, *uu, *vv;
+    const double *grid, *grids, *rhobar, *uu, *vv, *bvf;
     double *tend[9];
 };
 
@@ -49,7 +49,7 @@ __device__ __forceinline__ bool saturation_limit(const msgwam_params_t &p, doubl
                                                  double rr_st, double drr, double drr_st, double kk, double ll,
                                                  double mm, double mm_st, double dkk, double dll, double area,
                                                  const double *__restrict__ grids, const double *__restrict__ rhobar,
-                                                 double &maxd)
+                                                 const double *__restrict__ bvf, double &maxd)
 {
     const double rr_final = add(rr, mul(rr_st, dt));
     const double drr_final = add(drr, mul(drr_st, dt));
@@ -57,9 +57,10 @@ __device__ __forceinline__ bool saturation_limit(const msgwam_params_t &p, doubl
     const double dmm_final = dvd(area, drr_final);
     const double rho = interp1(rr_final, grids, rhobar, p.G, p.inv_dz_grids);
     const double kh2 = add(mul(kk, kk), mul(ll, ll));
-    const double omh = omega_from(kh2, mul(mm, mm), p.f0sq, p.n2);
+    const double omh = omega_from(kh2, mul(mm, mm), p.f0sq, n2_at(bvf, grids, p.G, p.inv_dz_grids, p.n2, rr));      // ext: N at rr_center
     const double psv = mul(mul(dkk, dll), dmm_final);
-    maxd = dvd(dvd(mul(mul(mul(p.k2half, rho), omh), p.n2), mul(mm_final, mm_final)), sub(mul(omh, omh), p.f0sq));
+    const double n2f = n2_at(bvf, grids, p.G, p.inv_dz_grids, p.n2, rr_final);                                    // ext: N at rr_final
+    maxd = dvd(dvd(mul(mul(mul(p.k2half, rho), omh), n2f), mul(mm_final, mm_final)), sub(mul(omh, omh), p.f0sq));
     return maxd < mul(dens, psv);
 }
 
@@ -75,21 +76,28 @@ __global__ void __launch_bounds__(NT) rhs_rays_kernel(const RhsArgs a)
         const double ff = mul(p.two_rot, sphi), f2 = mul(ff, ff);
         const double kh2 = add(mul(kk, kk), mul(ll, ll)), m2 = mul(mm, mm);
         const double vk = add(kh2, m2);
-        const double om = omega_from(kh2, m2, f2, p.n2);
-        const double cgr = dvd(dvd(mul(-mm, sub(mul(om, om), f2)), om), vk);      // L:448
+        const double n2 = n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, rr);     // ext: N^2 at the ray centre
+        const double om = omega_from(kh2, m2, f2, n2);
+        const double cgr = dvd(dvd(mul(-mm, sub(mul(om, om), f2)), om), vk);      // L:448 (at the centre)
+        double cgr_up = cgr, cgr_down = cgr;                                      // cg_rr ignores rr: up == down (L:635-636)
+        if (a.bvf != nullptr) {                                                   // ext: N at the two edges
+            const double hd = mul(.5, drr);
+            cgr_up = cg_rr_from(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, add(rr, hd)));
+            cgr_down = cg_rr_from(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, sub(rr, hd)));
+        }
         double du_ray, dv_ray;
         shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
         double cgl = 0.0, cgp = 0.0;
         if (p.hprop) {                                                            // L:400-405, 424-429
             const double uu_ray = interp1(rr, a.grids, a.uu, G, p.inv_dz_grids);
             const double vv_ray = interp1(rr, a.grids, a.vv, G, p.inv_dz_grids);
-            const double nd = sub(p.n2, mul(om, om));
+            const double nd = sub(n2, mul(om, om));
             cgl = add(mul(dvd(dvd(kk, om), vk), nd), uu_ray);
             cgp = add(mul(dvd(dvd(ll, om), vk), nd), vv_ray);
         }
         const double rad = add(p.rad_earth, rr);
-        const double drr_st = mul(.5, add(cgr, cgr));                             // L:640
-        const double ddrr_st = sub(cgr, cgr);                                     // L:641
+        const double drr_st = mul(.5, add(cgr_down, cgr_up));                     // L:640
+        const double ddrr_st = sub(cgr_up, cgr_down);                             // L:641
         double dkk_st = 0.0, dll_st = 0.0;
         if (p.hprop) {
             const double tphi = tan(phi);
@@ -103,10 +111,16 @@ __global__ void __launch_bounds__(NT) rhs_rays_kernel(const RhsArgs a)
             dll_st = sub(dvd(-sum, rad), g_phi);                                  // L:494-497
         }
         const double g_rr = add(mul(kk, du_ray), mul(ll, dv_ray));                // L:517
-        const double dmm_st = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), g_rr);   // L:519-520
+        double dmm_st = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), g_rr);     // L:519-520
+        if (a.bvf != nullptr) {                                                   // ext: - N N' (k^2 + l^2) / om / |k|^2
+            const double nr = interp1(rr, a.grids, a.bvf, G, p.inv_dz_grids);
+            double dnr, unused;
+            shear_interp(rr, a.grid, a.bvf, a.bvf, G, p.dz_grid, p.inv_dz_grid, dnr, unused);
+            dmm_st = sub(dmm_st, dvd(dvd(mul(mul(nr, dnr), kh2), om), vk));
+        }
         double maxd;
         const bool hit = saturation_limit(p, p.dt, dens, rr, drr_st, drr, ddrr_st, kk, ll, mm, dmm_st,
-                                          a.r.dkk[i], a.r.dll[i], a.r.rr_mm_area[i], a.grids, a.rhobar, maxd);
+                                          a.r.dkk[i], a.r.dll[i], a.r.rr_mm_area[i], a.grids, a.rhobar, a.bvf, maxd);
         const double st = hit ? dvd(sub(maxd, dens), p.dt) : 0.0;                 // L:612-615
         a.tend[0][i] = mul(p.saturate_online ? 1.0 : 0.0, st);                    // L:647
         a.tend[1][i] = dvd(dvd(cgl, rad), cphi);                                  // L:638
@@ -130,6 +144,7 @@ struct ProjArgs {
     const double *grid;
     int ng;
     double dz, rdz;
+    const double *bvf, *bvf_grids;      // extension: N on the staggered grid (p.G points) or NULL
     double *out;
 };
 
@@ -183,7 +198,8 @@ __global__ void __launch_bounds__(NT) project_kernel(const ProjArgs a)
                 else {
                     const double kk = a.kk[i], ll = a.ll[i];
                     const double ff = mul(a.p.two_rot, sin(a.phi[i]));
-                    const double cgr = cg_rr_from(add(mul(kk, kk), mul(ll, ll)), mul(.5, add(ml, mu)), mul(ff, ff), a.p.n2);
+                    const double n2 = n2_at(a.bvf, a.bvf_grids, a.p.G, a.p.inv_dz_grids, a.p.n2, mul(.5, add(rl, ru)));
+                    const double cgr = cg_rr_from(add(mul(kk, kk), mul(ll, ll)), mul(.5, add(ml, mu)), mul(ff, ff), n2);
                     if (a.var == 0) { v0 = mul(mul(cgr, kk), dens); v1 = mul(mul(cgr, ll), dens); }   // L:148-149
                     else v0 = mul(cgr, dens);                                    // L:167
                 }
@@ -210,7 +226,8 @@ __global__ void __launch_bounds__(NT) project_iface_kernel(const ProjArgs a)
         const double psv = fabs(mul(mul(a.dkk[i], a.dll[i]), a.dmm[i]));
         const double kk = a.kk[i], ll = a.ll[i], dens = a.dens[i];
         const double ff = mul(a.p.two_rot, sin(a.phi[i]));
-        const double cgr = cg_rr_from(add(mul(kk, kk), mul(ll, ll)), mul(.5, add(a.ma[i], a.mb[i])), mul(ff, ff), a.p.n2);
+        const double n2 = n2_at(a.bvf, a.bvf_grids, a.p.G, a.p.inv_dz_grids, a.p.n2, mul(.5, add(a.ra[i], a.rb[i])));
+        const double cgr = cg_rr_from(add(mul(kk, kk), mul(ll, ll)), mul(.5, add(a.ma[i], a.mb[i])), mul(ff, ff), n2);
         const int b0 = max(nlow + 1, 1), b1 = min(nup - 1, a.ng - 2);
         if (a.var == 3) {
             const double t = mul(mul(cgr, dens), psv);
@@ -267,7 +284,7 @@ __global__ void rk_update_kernel(int stage, double dt, const double *__restrict_
 struct SatArgs {
     msgwam_params_t p;
     int64_t n; int direct;
-    const double *dens, *rr, *rr_st, *drr, *drr_st, *kk, *ll, *mm, *mm_st, *dkk, *dll, *area, *grids, *rhobar;
+    const double *dens, *rr, *rr_st, *drr, *drr_st, *kk, *ll, *mm, *mm_st, *dkk, *dll, *area, *grids, *rhobar, *bvf;
     double *out;
 };
 
@@ -277,7 +294,7 @@ __global__ void __launch_bounds__(NT) saturation_kernel(const SatArgs a)
         double maxd;
         const double dens = a.dens[i];
         const bool hit = saturation_limit(a.p, a.p.dt, dens, a.rr[i], a.rr_st[i], a.drr[i], a.drr_st[i], a.kk[i], a.ll[i],
-                                          a.mm[i], a.mm_st[i], a.dkk[i], a.dll[i], a.area[i], a.grids, a.rhobar, maxd);
+                                          a.mm[i], a.mm_st[i], a.dkk[i], a.dll[i], a.area[i], a.grids, a.rhobar, a.bvf, maxd);
         if (a.direct) a.out[i] = hit ? maxd : dens;                               // L:606-610
         else a.out[i] = hit ? dvd(sub(maxd, dens), a.p.dt) : 0.0;                 // L:612-615
     }
@@ -287,7 +304,7 @@ __global__ void __launch_bounds__(NT) saturation_kernel(const SatArgs a)
 struct PwArgs {
     msgwam_params_t p;
     int op; int64_t n;
-    const double *kk, *ll, *mm, *phi, *rr, *grid, *grids, *uu, *vv;
+    const double *kk, *ll, *mm, *phi, *rr, *grid, *grids, *uu, *vv, *bvf;
     double f, f2;
     double *out;
 };
@@ -317,14 +334,15 @@ __global__ void __launch_bounds__(NT) pointwise_kernel(const PwArgs a)
             const double ff = mul(p.two_rot, sphi);
             f2 = mul(ff, ff);
         }
-        const double om = omega_from(kh2, m2, f2, p.n2);
+        const double n2 = (a.bvf != nullptr) ? n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, a.rr[i]) : p.n2;   // ext
+        const double om = omega_from(kh2, m2, f2, n2);
         if (a.op == MSGWAM_OP_OMEGA || a.op == MSGWAM_OP_OMEGA_F) { a.out[i] = om; continue; }
         const double cgr = dvd(dvd(mul(-mm, sub(mul(om, om), f2)), om), vk);
         if (a.op == MSGWAM_OP_CG_RR) { a.out[i] = cgr; continue; }
         const double rr = a.rr[i];
         double cgl = 0.0, cgp = 0.0;
         if (p.hprop) {
-            const double nd = sub(p.n2, mul(om, om));
+            const double nd = sub(n2, mul(om, om));
             cgl = add(mul(dvd(dvd(kk, om), vk), nd), interp1(rr, a.grids, a.uu, G, p.inv_dz_grids));
             cgp = add(mul(dvd(dvd(ll, om), vk), nd), interp1(rr, a.grids, a.vv, G, p.inv_dz_grids));
         }
@@ -334,7 +352,14 @@ __global__ void __launch_bounds__(NT) pointwise_kernel(const PwArgs a)
         if (a.op == MSGWAM_OP_DM_DT) {
             double du_ray, dv_ray;
             shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
-            a.out[i] = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), add(mul(kk, du_ray), mul(ll, dv_ray)));
+            double dm = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), add(mul(kk, du_ray), mul(ll, dv_ray)));
+            if (a.bvf != nullptr) {                                               // ext
+                const double nr = interp1(rr, a.grids, a.bvf, G, p.inv_dz_grids);
+                double dnr, unused;
+                shear_interp(rr, a.grid, a.bvf, a.bvf, G, p.dz_grid, p.inv_dz_grid, dnr, unused);
+                dm = sub(dm, dvd(dvd(mul(mul(nr, dnr), kh2), om), vk));
+            }
+            a.out[i] = dm;
             continue;
         }
         if (!p.hprop) { a.out[i] = 0.0; continue; }                               // L:470-471, 498-499
@@ -402,7 +427,7 @@ int msgwam_rhs_rays(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t
     if (n > 0) {
         RhsArgs a{};
         a.p = *p; a.r = *rays; a.n = n;
-        a.grid = grid->grid; a.grids = grid->grids; a.rhobar = grid->rhobar; a.uu = d_uu; a.vv = d_vv;
+        a.grid = grid->grid; a.grids = grid->grids; a.rhobar = grid->rhobar; a.uu = d_uu; a.vv = d_vv; a.bvf = grid->bvf;
         for (int f = 0; f < 9; ++f) { if (!d_tend[f]) return MSGWAM_E_BADARG; a.tend[f] = d_tend[f]; }
         rhs_rays_kernel<<<grid_for(n, NT, 8), NT, 0, s>>>(a);
         cudaError_t e = cudaGetLastError();
@@ -414,6 +439,7 @@ int msgwam_rhs_rays(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t
     q.dens = rays->dens; q.phi = rays->phi; q.ra = rays->rr; q.rb = rays->drr; q.kk = rays->kk; q.ll = rays->ll;
     q.ma = rays->mm; q.mb = rays->dmm; q.dkk = rays->dkk; q.dll = rays->dll; q.dmm = rays->dmm;
     q.grid = grid->grids; q.ng = p->G; q.dz = p->dz_grids; q.rdz = p->inv_dz_grids; q.out = d_proj;
+    q.bvf = grid->bvf; q.bvf_grids = grid->grids;
     if (n > 0) {
         return launch_project(q, n, s);
     }
@@ -455,8 +481,8 @@ int msgwam_rk_update(int32_t stage, double dt, const double *d_tend, double *d_q
 int msgwam_wave_projection(int32_t var, const msgwam_params_t *p, int64_t n, const double *d_dens, const double *d_phi,
                            const double *d_rr_low, const double *d_rr_up, const double *d_kk, const double *d_ll,
                            const double *d_mm_low, const double *d_mm_up, const double *d_dkk, const double *d_dll,
-                           const double *d_dmm, const double *d_grid, int32_t ng, double dz, double inv_dz, double *d_out,
-                           void *stream)
+                           const double *d_dmm, const double *d_grid, int32_t ng, double dz, double inv_dz,
+                           const double *d_bvf, const double *d_bvf_grids, double *d_out, void *stream)
 {
     if (!p || var < 0 || var > 4 || n < 0 || ng < 3 || !d_grid || !d_out) return MSGWAM_E_BADARG;
     if (n > 0 && (!d_dens || !d_phi || !d_rr_low || !d_rr_up || !d_kk || !d_ll || !d_mm_low || !d_mm_up || !d_dkk ||
@@ -474,6 +500,8 @@ int msgwam_wave_projection(int32_t var, const msgwam_params_t *p, int64_t n, con
     q.dens = d_dens; q.phi = d_phi; q.ra = d_rr_low; q.rb = d_rr_up; q.kk = d_kk; q.ll = d_ll;
     q.ma = d_mm_low; q.mb = d_mm_up; q.dkk = d_dkk; q.dll = d_dll; q.dmm = d_dmm;
     q.grid = d_grid; q.ng = ng; q.out = d_out;
+    q.bvf = d_bvf; q.bvf_grids = d_bvf_grids;
+    if ((d_bvf == nullptr) != (d_bvf_grids == nullptr)) return MSGWAM_E_BADARG;
     q.dz = dz; q.rdz = inv_dz;
     if (var >= 3) {
         project_iface_kernel<<<grid_for(n, NT, 8), NT, 0, s>>>(q);
@@ -486,7 +514,7 @@ int msgwam_saturation(const msgwam_params_t *p, int64_t n, int32_t direct, const
                       const double *d_rr_st, const double *d_drr, const double *d_drr_st, const double *d_kk,
                       const double *d_ll, const double *d_mm, const double *d_mm_st, const double *d_dkk,
                       const double *d_dll, const double *d_area, const double *d_grids, const double *d_rhobar,
-                      double *d_out, void *stream)
+                      const double *d_bvf, double *d_out, void *stream)
 {
     if (!p || n < 0) return MSGWAM_E_BADARG;
     if (n == 0) return 0;
@@ -496,7 +524,7 @@ int msgwam_saturation(const msgwam_params_t *p, int64_t n, int32_t direct, const
     int rc = props();
     if (rc) return rc;
     SatArgs a{*p, n, direct, d_dens, d_rr, d_rr_st, d_drr, d_drr_st, d_kk, d_ll, d_mm, d_mm_st, d_dkk, d_dll, d_area,
-              d_grids, d_rhobar, d_out};
+              d_grids, d_rhobar, d_bvf, d_out};
     saturation_kernel<<<grid_for(n, NT, 8), NT, 0, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
@@ -517,7 +545,8 @@ int msgwam_pointwise(int32_t op, const msgwam_params_t *p, int64_t n, const doub
     if (rc) return rc;
     PwArgs a{};
     a.p = *p; a.op = op; a.n = n; a.kk = d_kk; a.ll = d_ll; a.mm = d_mm; a.phi = d_phi; a.rr = d_rr;
-    if (grid) { a.grid = grid->grid; a.grids = grid->grids; }
+    if (grid) { a.grid = grid->grid; a.grids = grid->grids; a.bvf = grid->bvf; }
+    if (a.bvf && (!d_rr || !a.grids || !a.grid || p->G < 3)) return MSGWAM_E_BADARG;     // the profile needs a position
     a.uu = d_uu; a.vv = d_vv; a.f = f; a.f2 = f2; a.out = d_out;
     pointwise_kernel<<<grid_for(n, NT, 8), NT, 0, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();

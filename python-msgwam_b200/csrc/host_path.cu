@@ -74,7 +74,7 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
     msgwam_rays_t r{};
     r.dens = d_dens; r.phi = d_phi; r.rr = d_rr; r.drr = d_drr; r.kk = d_kk; r.ll = d_ll; r.mm = d_mm; r.dmm = d_dmm;
     r.dkk = d_dkk; r.dll = d_dll; r.ff = d_ff; r.pkl = d_pkl;
-    msgwam_grid_t gr{d_grid, d_grids, d_rho, d_pg};
+    msgwam_grid_t gr{d_grid, d_grids, d_rho, d_pg, nullptr};
     rc = msgwam_column_step(p, &r, n, &gr, d_uu, d_vv, d_work, d_rro, d_mmo, d_uuo, d_vvo, stream);
     if (rc) return rc;
     if (n > 0) {

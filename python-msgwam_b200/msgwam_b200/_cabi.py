@@ -46,7 +46,7 @@ class Peers(ctypes.Structure):
 
 
 class Grid(ctypes.Structure):
-    _fields_ = [(k, c_void_p) for k in ("grid", "grids", "rhobar", "pg")]
+    _fields_ = [(k, c_void_p) for k in ("grid", "grids", "rhobar", "pg", "bvf")]
 
 
 OP_OMEGA, OP_OMEGA_F, OP_CG_RR, OP_CG_LAMBDA, OP_CG_PHI, OP_DK_DT, OP_DL_DT, OP_DM_DT, OP_GRADIENTS = range(9)
@@ -74,8 +74,8 @@ SIGNATURES = {
     "msgwam_grid_tendency": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_mean_flow_tendency": (ctypes.c_int, [_i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_rk_update": (ctypes.c_int, [_i32, _dbl, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "msgwam_wave_projection": (ctypes.c_int, [_i32, _PP, _i64] + [_vp] * 12 + [_i32, _dbl, _dbl, _vp, _vp]),
-    "msgwam_saturation": (ctypes.c_int, [_PP, _i64, _i32] + [_vp] * 15 + [_vp]),
+    "msgwam_wave_projection": (ctypes.c_int, [_i32, _PP, _i64] + [_vp] * 12 + [_i32, _dbl, _dbl, _vp, _vp, _vp, _vp]),
+    "msgwam_saturation": (ctypes.c_int, [_PP, _i64, _i32] + [_vp] * 16 + [_vp]),
     "msgwam_pointwise": (ctypes.c_int, [_i32, _PP, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _GP, _vp, _vp, _vp, _vp]),
     "msgwam_compact_scratch_bytes": (_i64, [_i64]),
     "msgwam_flag_rays": (ctypes.c_int, [_PP, _i64, _vp, _vp, _vp, _dbl, _vp, _vp]),
@@ -83,6 +83,9 @@ SIGNATURES = {
     "msgwam_host_stage_doubles": (_i64, [_i64, _i32]),
     "msgwam_rk3_column_host": (ctypes.c_int, [_PP, _i64, ctypes.POINTER(_vp)] + [_vp] * 14 + [_vp]),
 }
+
+
+ABI_VERSION = 2          # MSGWAM_ABI_VERSION of include/msgwam_b200.h
 
 
 def _load():
@@ -95,7 +98,7 @@ def _load():
         fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.msgwam_abi_version() != 1:
+    if lib.msgwam_abi_version() != ABI_VERSION:
         raise ImportError("msgwam_b200: ABI version mismatch in %s" % LIB_PATH)
     return lib
 
@@ -126,7 +129,9 @@ def snapshot_params(dt, *, bvf, phi0, kappa, saturate_online, hprop, grid, grids
     """
     p = Params()
     p.dt = float(dt)
-    p.n2 = bvf ** 2                                     # L:383
+    # extension: an array-valued bvf is a profile on grids, handed to the kernels through
+    # msgwam_grid_t.bvf; the scalar must never be used then
+    p.n2 = float("nan") if np.ndim(bvf) > 0 else bvf ** 2    # L:383
     p.two_rot = 2 * rot_earth                           # L:382
     p.rad_earth = rad_earth
     p.c8rot2 = 8 * rot_earth ** 2                       # L:491

@@ -97,21 +97,25 @@ class Engine:
             self._stage[key] = s
         return s
 
-    def grid_on_device(self, grid, grids, rhobar, pg):
-        """Device copies of the four background profiles, re-uploaded only when their values change."""
+    def grid_on_device(self, grid, grids, rhobar, pg, bvf=None):
+        """Device copies of the background profiles, re-uploaded only when their values change.  bvf: None for
+        the reference's scalar N, or (extension) the N profile on grids."""
         G = len(grids)
         host = (np.ascontiguousarray(grid, dtype=np.float64), np.ascontiguousarray(grids, dtype=np.float64),
                 np.ascontiguousarray(np.broadcast_to(np.asarray(rhobar, dtype=np.float64), (G,))),
                 np.ascontiguousarray(pg, dtype=np.float64).reshape(2, G))
+        if bvf is not None:
+            host = host + (np.ascontiguousarray(bvf, dtype=np.float64).reshape(G),)
         c = self._grid_cache.get(G)
-        if c is not None and all(np.array_equal(a, b) for a, b in zip(c[0], host)):
+        if c is not None and len(c[0]) == len(host) and all(np.array_equal(a, b) for a, b in zip(c[0], host)):
             return c[1]
         devs = tuple(self.torch.from_numpy(a.copy()).to(self.device) for a in host)
         self._grid_cache[G] = (tuple(a.copy() for a in host), devs)
         return devs
 
     def grid_struct(self, devs) -> Grid:
-        return Grid(self.ptr(devs[0]), self.ptr(devs[1]), self.ptr(devs[2]), self.ptr(devs[3]))
+        return Grid(self.ptr(devs[0]), self.ptr(devs[1]), self.ptr(devs[2]), self.ptr(devs[3]),
+                    self.ptr(devs[4]) if len(devs) > 4 else _vp(0))
 
     def derived_statics(self, phi, dkk, dll, two_rot):
         """ff = 2*ROT*sin(phi), pkl = dkk*dll on the device; cached on (storage, version) of the inputs."""

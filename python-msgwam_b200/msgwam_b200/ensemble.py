@@ -53,6 +53,8 @@ class RayEnsemble:
         self.grid_devs = tuple(eng.dev(a) for a in (self.grid_host, self.grids_host,
                                                     np.broadcast_to(np.asarray(rhobar, dtype=np.float64), (self.G,)),
                                                     np.asarray(pressure_gradient, dtype=np.float64).reshape(2, self.G)))
+        if np.ndim(bvf) > 0:                        # extension: N profile on grids (general path only)
+            self.grid_devs = self.grid_devs + (eng.dev(np.asarray(bvf, dtype=np.float64).reshape(self.G)),)
         self.uu, self.vv = eng.dev(uu, self.G).clone(), eng.dev(vv, self.G).clone()
         self._uu2, self._vv2 = eng.empty(self.G), eng.empty(self.G)
         self.work = eng.zeros(int(lib.msgwam_column_work_doubles(self.G)))
@@ -100,7 +102,7 @@ class RayEnsemble:
         eng = self.eng
         p = self.params(dt)
         g = eng.grid_struct(self.grid_devs)
-        column = not p.hprop and not p.saturate_online
+        column = not p.hprop and not p.saturate_online and len(self.grid_devs) == 4
         nc = self.G - 1
         for _ in range(nsteps):
             if column:

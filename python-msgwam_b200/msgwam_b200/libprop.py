@@ -158,11 +158,18 @@ def _size(*xs):
     return 1
 
 
+def _bvf_profile():
+    """EXTENSION (not in the reference): model_config['bvf'] may be an array of N on
+    `grids` instead of the reference's scalar.  Returns that array, or None for the reference's behaviour."""
+    b = model_config['bvf']
+    return b if np.ndim(b) > 0 else None
+
+
 def _grid_devs(eng):
     if np.ndim(pressure_gradient) == 0:
         # the reference indexes pressure_gradient[0] (L:537): a scalar raises TypeError there as well
         raise TypeError("pressure_gradient is not set (call set_pressure_gradient first)")
-    return eng.grid_on_device(grid, grids, rhobar, pressure_gradient)
+    return eng.grid_on_device(grid, grids, rhobar, pressure_gradient, _bvf_profile())
 
 
 def _pack11(slots):
@@ -181,12 +188,14 @@ def _pointwise(op, kk, ll, mm, phi, rr, uu, vv, f=0.0, f2=0.0, need_grid=False, 
     n = _size(*[x for x in (kk, ll, mm, phi, rr) if x is not None])
     d = lambda x: None if x is None else eng.dev(x, n)
     tk, tl, tm, tp, tr = d(kk), d(ll), d(mm), d(phi), d(rr)
-    if need_grid:
+    prof = _bvf_profile()
+    if need_grid or prof is not None:
         p = _params()
         G = p.G
-        gd = eng.grid_on_device(grid, grids, rhobar, pressure_gradient if np.ndim(pressure_gradient) else np.zeros((2, G)))
+        gd = eng.grid_on_device(grid, grids, rhobar, pressure_gradient if np.ndim(pressure_gradient) else np.zeros((2, G)),
+                                prof)
         g = eng.grid_struct(gd)
-        tu, tv = eng.dev(uu, G), eng.dev(vv, G)
+        tu, tv = (eng.dev(uu, G), eng.dev(vv, G)) if need_grid else (None, None)
     else:
         p = _params_nogrid()
         g, tu, tv = None, None, None
@@ -198,17 +207,29 @@ def _pointwise(op, kk, ll, mm, phi, rr, uu, vv, f=0.0, f2=0.0, need_grid=False, 
     return _out(eng, out, like_dev)
 
 
-def omega(kk, ll, mm, phi):
-    """Intrinsic frequency sqrt((N^2 (k^2+l^2) + f^2 m^2) / |k|^2).  L:369-383"""
+def _position(rr):
+    """The height argument matters only to the N(z) extension; with the reference's scalar bvf it is dropped
+    (L:434-448 ignores it)."""
+    if _bvf_profile() is None:
+        return None
+    if rr is None:
+        raise TypeError("model_config['bvf'] is a profile: omega() needs the height argument rr")
+    return rr
+
+
+def omega(kk, ll, mm, phi, rr=None):
+    """Intrinsic frequency sqrt((N^2 (k^2+l^2) + f^2 m^2) / |k|^2).  L:369-383
+    (`rr` is only read by the N(z) extension; the reference signature has no such argument.)"""
     if np.ndim(phi) == 0 and not hasattr(phi, "is_cuda"):
         f = 2 * ROT_EARTH * np.sin(phi)            # numpy scalar, squared with the scalar power (L:382-383)
-        return _pointwise(_cabi.OP_OMEGA_F, kk, ll, mm, None, None, None, None, f=f, f2=f ** 2)
-    return _pointwise(_cabi.OP_OMEGA, kk, ll, mm, phi, None, None, None)
+        return _pointwise(_cabi.OP_OMEGA_F, kk, ll, mm, None, _position(rr), None, None, f=f, f2=f ** 2)
+    return _pointwise(_cabi.OP_OMEGA, kk, ll, mm, phi, _position(rr), None, None)
 
 
 def cg_rr(kk, ll, mm, lam, phi, rr):
-    """Vertical group velocity -m (om^2 - f^2) / om / |k|^2 (lam and rr are ignored, as in L:434-448)."""
-    return _pointwise(_cabi.OP_CG_RR, kk, ll, mm, phi, None, None, None)
+    """Vertical group velocity -m (om^2 - f^2) / om / |k|^2 (lam and rr are ignored, as in L:434-448;
+    the N(z) extension evaluates N at rr)."""
+    return _pointwise(_cabi.OP_CG_RR, kk, ll, mm, phi, _position(rr), None, None)
 
 
 def cg_lambda(kk, ll, mm, lam, phi, rr, uu, vv):
@@ -306,9 +327,14 @@ def wave_projection(dens, lam, phi, rr_low, rr_up, kk, ll, mm_low, mm_up, dkk, d
     dz = float(np.diff(g01)[0])                                     # L:123
     shape = {0: (2, ng - 1), 1: (ng - 1,), 2: (ng - 1,), 3: (ng,), 4: (2, ng)}[var]
     out = eng.empty(*shape)
-    p = _params_nogrid()
+    prof = _bvf_profile()
+    if prof is None:
+        p, tb, tbg = _params_nogrid(), None, None
+    else:                                                           # extension: N lives on the module's grids
+        p = _params()
+        tb, tbg = eng.dev(prof, p.G), eng.dev(grids, p.G)
     check(lib.msgwam_wave_projection(var, p, n, *[eng.ptr(a) for a in arrs], eng.ptr(g), ng, dz, 1.0 / dz,
-                                     eng.ptr(out), eng.stream), "msgwam_wave_projection")
+                                     eng.ptr(tb), eng.ptr(tbg), eng.ptr(out), eng.stream), "msgwam_wave_projection")
     eng.launches += 2
     return _out(eng, out, like_dev)
 
@@ -330,8 +356,10 @@ def saturation(dt, dens, rr_center, rr_center_st, drr, drr_st, kk, ll, mm_center
     gs = eng.dev(grids, G)
     rho = eng.dev(np.broadcast_to(np.asarray(rhobar, dtype=np.float64), (G,)) if not eng.is_dev(rhobar) else rhobar, G)
     out = eng.empty(n)
+    prof = _bvf_profile()
+    tb = None if prof is None else eng.dev(prof, G)
     check(lib.msgwam_saturation(p, n, int(bool(direct)), *[eng.ptr(a) for a in arrs], eng.ptr(gs), eng.ptr(rho),
-                                eng.ptr(out), eng.stream), "msgwam_saturation")
+                                eng.ptr(tb), eng.ptr(out), eng.stream), "msgwam_saturation")
     eng.launches += 1
     return _out(eng, out, like_dev)
 
@@ -447,7 +475,7 @@ def RK3(dt, var):
     eng = _engine()
     p = _params(dt)
     like_dev = _any_dev(eng, *var)
-    column = not p.hprop and not p.saturate_online
+    column = not p.hprop and not p.saturate_online and _bvf_profile() is None
     if column and not like_dev:
         return _rk3_numpy_column(eng, p, var)
     n = _size(var[3])

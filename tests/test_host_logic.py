@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for nm in names:
         assert hasattr(lib, nm), nm
         assert nm in _cabi.SIGNATURES, "binding missing for " + nm
-    assert lib.msgwam_abi_version() == 1
+    assert lib.msgwam_abi_version() == _cabi.ABI_VERSION
     assert b"bad argument" in _cabi.lib.msgwam_error_string(-1)
     assert _cabi.lib.msgwam_column_work_doubles(1000) >= 6 * 999
     assert _cabi.lib.msgwam_host_stage_doubles(1000, 100) > 14 * 1000

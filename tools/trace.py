@@ -25,7 +25,7 @@ for n in (1000000,):
     base = int(lib.msgwam_column_work_doubles(ens.G)) - 2 * 160 * 16 - 16
     tr = ens.work[base:base + 2 * 160 * 16].cpu().numpy().reshape(2, 160, 16)[:, :148]
     gm = ens.work[base + 2 * 160 * 16:].cpu().numpy()
-    print('chain phases (cycles): load %d tables0 %d chain0 %d tables1 %d chain1 %d tables2 %d' % tuple(gm[k + 1] - gm[k] for k in range(6)))
+    pass
     names = ["prologue", "sweep", "winflush", "histflush", "ticket", "tail", "end"]
     for ps in (0, 1):
         t = tr[ps]

@@ -233,7 +233,10 @@ def run_ours(args, rank, local_rank, world):
         if world == 1:   # the call libprop.RK3 / RayEnsemble.step make on one GPU: two launches, finish fused as pass B's tail
             check(lib.msgwam_column_step(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out),
                                          P(uu_out), P(vv_out), eng.stream), "column_step")
-        else:
+        elif exchange is not None:   # several GPUs: still two launches; the all-reduces run in the sweeps' tails over NVLink
+            check(lib.msgwam_column_step_p2p(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out),
+                                             P(uu_out), P(vv_out), exchange.next(2), eng.stream), "column_step_p2p")
+        else:                        # NCCL fallback: all-reduces between the kernels
             pass_a(); reduce_(ens.work[:4 * nc]); pass_b(); reduce_(ens.work[4 * nc:6 * nc]); finish()
 
     def barrier():
@@ -265,7 +268,7 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_steps = float(tt.item())
-    launches = (2 if world == 1 else (4 if exchange is not None else 3)) * args.steps
+    launches = (2 if (world == 1 or exchange is not None) else 3) * args.steps
 
     # ---- per-kernel timing for the roofline (single rank's kernels; no collectives inside) --------
     ka, kb, kf = [], [], []
@@ -347,7 +350,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": "configs[1]: 1e6 ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000",
                    "rays_per_gpu": n, "grid_levels": ens.G, "dt_s": sc.dt, "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": "rays sharded, %d rank(s); all-reduce of the deposited flux twice per step (%s)" % (
-                       world, "none needed" if world == 1 else ("one-shot pushes over NVLink peer memory: a one-CTA kernel before pass B, fused into the finish kernel" if exchange is not None else "NCCL")),
+                       world, "none needed" if world == 1 else ("one-shot pushes over NVLink peer memory, fused into the tails of the two sweeps" if exchange is not None else "NCCL")),
                    "mode": "M1 coupled (reference RK3 semantics: mean flow inside the RK state), 2 ray sweeps per step"},
         "roofline": {"bound": "hbm", "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak,
                      "traffic": NCU_TRAFFIC_PASS_B_PER_RAY * n, "traffic_source": "ncu --set full, profiles/r01_column_pass_ncu_full_summary.json (75.4 B/ray at 1e6 rays)",

@@ -138,6 +138,13 @@ int msgwam_column_pass_b_p2p(const msgwam_params_t *p, const msgwam_rays_t *rays
 int msgwam_column_finish_p2p(const msgwam_params_t *p, const msgwam_grid_t *grid,
                              const double *d_uu, const double *d_vv, double *d_work,
                              double *d_uu_out, double *d_vv_out, const msgwam_peers_t *peers, void *stream);
+/* Multi-GPU, fully fused: the same two launches as msgwam_column_step; the last CTA of each sweep all-reduces this
+ * GPU's deposit over the peer inboxes (epochs peers->epoch and peers->epoch + 1: advance the epoch by TWO per
+ * call) before the mean-flow chain (inside pass B) / the finish (tail of pass B) run on the sums. */
+int msgwam_column_step_p2p(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                           const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                           double *d_work, double *d_rr_out, double *d_mm_out,
+                           double *d_uu_out, double *d_vv_out, const msgwam_peers_t *peers, void *stream);
 /* offset (in doubles) inside d_work of the error word set by a timed-out peer exchange (0.0 = ok) */
 int64_t msgwam_column_error_offset(int32_t G);
 

@@ -150,12 +150,12 @@ class Engine:
         mm_out = self.empty(n) if mm_out is None else mm_out
         uu_out, vv_out = self.empty(p.G), self.empty(p.G)
         s = self.stream
-        if exchange is not None:
-            check(lib.msgwam_column_pass_a(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), s), "msgwam_column_pass_a")
-            check(lib.msgwam_column_pass_b_p2p(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
-                                               self.ptr(mm_out), exchange.next(), s), "msgwam_column_pass_b_p2p")
-            check(lib.msgwam_column_finish_p2p(p, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(uu_out),
-                                               self.ptr(vv_out), exchange.next(), s), "msgwam_column_finish_p2p")
+        if exchange is not None:        # two launches; the all-reduces run in the sweeps' tails over NVLink peer memory
+            check(lib.msgwam_column_step_p2p(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
+                                             self.ptr(mm_out), self.ptr(uu_out), self.ptr(vv_out), exchange.next(2), s),
+                  "msgwam_column_step_p2p")
+            self.launches += 2
+            return rr_out, mm_out, uu_out, vv_out
         elif reduce_fn is None:
             check(lib.msgwam_column_step(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
                                          self.ptr(mm_out), self.ptr(uu_out), self.ptr(vv_out), s), "msgwam_column_step")

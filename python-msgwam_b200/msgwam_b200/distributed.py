@@ -15,8 +15,8 @@ from ._engine import Engine
 
 
 class PeerExchange:
-    """Symmetric-memory inboxes for the all-reduce that is fused into the chain / finish kernels
-    (csrc/column_step.cu: p2p_allreduce).  One instance per (G, process group); `next()` hands out the
+    """Symmetric-memory inboxes for the all-reduce that is fused into the tails of the two sweeps
+    (csrc/column_step.cu: p2p_allreduce, msgwam_column_step_p2p).  One instance per (G, process group); `next()` hands out the
     msgwam_peers_t of the next reduction -- the epoch sequence is identical on all ranks because every rank
     runs the same sequence of steps."""
 
@@ -56,10 +56,11 @@ class PeerExchange:
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.epoch = 0
 
-    def next(self):
-        self.epoch += 1
+    def next(self, count=1):
+        """msgwam_peers_t for the next `count` reductions (the struct carries the epoch of the first)."""
         pe = _cabi.Peers()
-        pe.world, pe.rank, pe.epoch = self.world, self.rank, self.epoch
+        pe.world, pe.rank, pe.epoch = self.world, self.rank, self.epoch + 1
+        self.epoch += count
         for r, ptr in enumerate(self.ptrs):
             pe.inbox[r] = ptr
         return pe

@@ -109,15 +109,17 @@ class RayEnsemble:
                 rays = self._rays()
                 s = eng.stream
                 rr, mm = self.field("rr"), self.field("mm")
-                check(lib.msgwam_column_pass_a(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work), s),
-                      "msgwam_column_pass_a")
-                if self.exchange is not None:       # all-reduce fused into the chain / finish kernels (peer memory)
-                    check(lib.msgwam_column_pass_b_p2p(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
-                                                       eng.ptr(rr), eng.ptr(mm), self.exchange.next(), s), "msgwam_column_pass_b_p2p")
-                    check(lib.msgwam_column_finish_p2p(p, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
-                                                       eng.ptr(self._uu2), eng.ptr(self._vv2), self.exchange.next(), s),
-                          "msgwam_column_finish_p2p")
-                else:
+                if self.exchange is not None:       # all-reduces fused into the tails of the two sweeps (peer memory)
+                    check(lib.msgwam_column_step_p2p(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
+                                                     eng.ptr(rr), eng.ptr(mm), eng.ptr(self._uu2), eng.ptr(self._vv2),
+                                                     self.exchange.next(2), s), "msgwam_column_step_p2p")
+                elif self.dist is None or self.dist.get_world_size() == 1:
+                    check(lib.msgwam_column_step(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
+                                                 eng.ptr(rr), eng.ptr(mm), eng.ptr(self._uu2), eng.ptr(self._vv2), s),
+                          "msgwam_column_step")
+                else:                               # NCCL all-reduces between the kernels
+                    check(lib.msgwam_column_pass_a(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work), s),
+                          "msgwam_column_pass_a")
                     self._reduce(self.work[:4 * nc])
                     check(lib.msgwam_column_pass_b(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
                                                    eng.ptr(rr), eng.ptr(mm), s), "msgwam_column_pass_b")

@@ -104,40 +104,61 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
     if (lo == INT_MAX) return;                                  // no lane has anything to deposit
     const int hi = __reduce_max_sync(FULL_MASK, ok ? nup : INT_MIN);
     const bool fits = (hi - lo) <= WIN;
-    if (w.live && (!fits || lo < w.wb || hi > w.wb + WIN)) window_flush(w, h0, h1);
+    bool inw = ok;
     if (fits) {
+        if (w.live && (lo < w.wb || hi > w.wb + WIN)) window_flush(w, h0, h1);
         if (!w.live) { w.wb = lo; w.live = 1; }
-        if (ok) {
-            // private column of the warp window: plain load / add / store.  The first four cells are
-            // unrolled so that their weight computations overlap (a ray volume rarely spans more).
-            double2 *col = w.cell + (nlow - w.wb) * 32 + (threadIdx.x & 31);
-            double t[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) t[k] = (nlow + k < nup) ? cell_weight(nlow + k, rl, ru, psv, dz, rdz, g) : 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (nlow + k < nup) {
-                    double2 a = col[k * 32];
-                    a.x = add(a.x, mul(t[k], v0)); a.y = add(a.y, mul(t[k], v1));
-                    col[k * 32] = a;
-                }
-            }
-            for (int c = nlow + 4; c < nup; ++c) {
-                const double tc = cell_weight(c, rl, ru, psv, dz, rdz, g);
-                double2 a = col[(c - nlow) * 32];
-                a.x = add(a.x, mul(tc, v0)); a.y = add(a.y, mul(tc, v1));
-                col[(c - nlow) * 32] = a;
+    } else {
+        // The warp as a whole does not fit: at r0 its rays sit within metres of each other, but by the later RK
+        // states a few fast ones have run several cells ahead (0.7 % of the warp iterations of pass B in the
+        // benchmark ensemble).  The window keeps serving the majority and only the lanes outside it add to the CTA
+        // histogram.  (Sending the whole warp there cost ~1e4 cycles per event -- 32 lanes in a CAS loop on the same
+        // few cells -- and those events decided when a CTA finished.)  Unordered rays: nearly every lane is outside.
+        const unsigned m_ok = __ballot_sync(FULL_MASK, ok);
+        if (w.live) {
+            inw = ok && nlow >= w.wb && nup <= w.wb + WIN;
+            if (2 * __popc(__ballot_sync(FULL_MASK, inw)) < __popc(m_ok)) window_flush(w, h0, h1);
+        }
+        if (!w.live) {
+            // anchor at the low end or at the high end, whichever serves more lanes (none if that is under half)
+            const int n_lo = __popc(__ballot_sync(FULL_MASK, ok && nup <= lo + WIN));
+            const int n_hi = __popc(__ballot_sync(FULL_MASK, ok && nlow >= hi - WIN));
+            const int wb = n_lo >= n_hi ? lo : hi - WIN;
+            inw = false;
+            if (2 * max(n_lo, n_hi) >= __popc(m_ok)) {
+                w.wb = wb; w.live = 1;
+                inw = ok && nlow >= wb && nup <= wb + WIN;
             }
         }
-    } else {
-        // scattered lanes (unordered rays): few collisions, add to the CTA histogram directly
-        if (used != nullptr && (threadIdx.x & 31) == 0) *used = 1;
-        if (ok) {
-            for (int c = nlow; c < nup; ++c) {
-                const double tc = cell_weight(c, rl, ru, psv, dz, rdz, g);
-                atomicAdd(s0 + c, mul(tc, v0));
-                atomicAdd(s1 + c, mul(tc, v1));
+    }
+    if (inw) {
+        // private column of the warp window: plain load / add / store.  The first four cells are
+        // unrolled so that their weight computations overlap (a ray volume rarely spans more).
+        double2 *col = w.cell + (nlow - w.wb) * 32 + (threadIdx.x & 31);
+        double t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = (nlow + k < nup) ? cell_weight(nlow + k, rl, ru, psv, dz, rdz, g) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (nlow + k < nup) {
+                double2 a = col[k * 32];
+                a.x = add(a.x, mul(t[k], v0)); a.y = add(a.y, mul(t[k], v1));
+                col[k * 32] = a;
             }
+        }
+        for (int c = nlow + 4; c < nup; ++c) {
+            const double tc = cell_weight(c, rl, ru, psv, dz, rdz, g);
+            double2 a = col[(c - nlow) * 32];
+            a.x = add(a.x, mul(tc, v0)); a.y = add(a.y, mul(tc, v1));
+            col[(c - nlow) * 32] = a;
+        }
+    } else if (ok) {
+        // outlier lane / unordered rays: add to the CTA histogram directly
+        if (used != nullptr) *used = 1;
+        for (int c = nlow; c < nup; ++c) {
+            const double tc = cell_weight(c, rl, ru, psv, dz, rdz, g);
+            atomicAdd(s0 + c, mul(tc, v0));
+            atomicAdd(s1 + c, mul(tc, v1));
         }
     }
 }

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MSGWAM_ABI_VERSION 2
+#define MSGWAM_ABI_VERSION 3
 
 #define MSGWAM_E_BADARG      (-1)   /* null pointer / negative size / inconsistent arguments   */
 #define MSGWAM_E_GRID_SIZE   (-2)   /* G too small (< 3) or too large for the fused column kernels */
@@ -66,6 +66,9 @@ typedef struct msgwam_rays {
     const double *dkk, *dll, *rr_mm_area;
     const double *ff;    /* 2*ROT_EARTH*sin(phi)   (msgwam_derive_statics; column mode only) */
     const double *pkl;   /* dkk*dll                (msgwam_derive_statics; column mode only) */
+    double *stage1;      /* column mode only: 3*n doubles of scratch.  Pass A leaves the stage-1 increments and the
+                            group velocity of state r1 there (dt*cg_rr(r0) | dt*dm_dt(r0) | cg_rr(r1)) so that
+                            pass B starts at RK stage 2 instead of recomputing stage 1.                           */
 } msgwam_rays_t;
 
 /* Background profiles on the 1-D mean-flow grid (L:6-9). */
@@ -95,15 +98,19 @@ int msgwam_derive_statics(const double *d_phi, const double *d_dkk, const double
  *      for HPROP_GLOBAL == False and saturate_online == False: only rr and mm change) --------
  *
  * The mean flow is part of the RK state, so stage s+1 needs the deposit of ALL rays at stage s:
- *   pass A : deposit D(r0); stage 1 with u0; deposit D(r1)                      (reads 9 fields)
+ *   pass A : deposit D(r0); stage 1 with u0; deposit D(r1); stage-1 increments and cg_rr(r1) -> rays->stage1
+ *            (reads 9 fields, writes 3)
  *   [multi-GPU: all-reduce D0|D1 here -- they are contiguous: 4*(G-1) doubles]
- *   pass B : stage 1 (recomputed), stage 2 with u1, deposit D(r2), stage 3 with u2; write rr, mm
+ *   pass B : prologue = the mean-flow half of RK stages 1-2 on the reduced D0, D1, distributed over the CTAs
+ *            (u1, u2 and the shear tables the sweep interpolates); then per ray r1 = r0 + stage-1 increment
+ *            (from rays->stage1), stage 2 with u1, deposit D(r2), stage 3 with u2; write rr, mm
+ *            (reads 12 fields, writes 2)
  *   [multi-GPU: all-reduce D2: 2*(G-1) doubles]
- *   finish : u3, v3 from u0, D0, D1, D2; zeroes the deposit buffers for the next step
+ *   finish : u3, v3 from u2 and D2; zeroes the deposit buffers for the next step
  * d_work: msgwam_column_work_doubles(G) doubles, zero-initialised by the caller once; layout
- * D0 (2,G-1) | D1 (2,G-1) | D2 (2,G-1) | shear tables and saved mean-flow stage (internal).
- * rr_out/mm_out may alias rays->rr / rays->mm.  msgwam_column_pass_b first launches a one-CTA kernel that
- * advances the mean-flow half of RK stages 1-2 and builds the shear tables the sweep interpolates.
+ * D0 (2,G-1) | D1 (2,G-1) | D2 (2,G-1) | shear tables and saved mean-flow stage | counters (internal).
+ * rr_out/mm_out may alias rays->rr / rays->mm.  msgwam_column_pass_b must follow msgwam_column_pass_a on the same
+ * stream (pass A arms the counter pass B's CTAs meet on and fills rays->stage1).
  */
 int64_t msgwam_column_work_doubles(int32_t G);
 /* largest G (= len(grids)) the fused column kernels accept on this device: the shear tables of the three

@@ -27,8 +27,9 @@ static inline int64_t pad32(int64_t n) { return (n + 31) & ~(int64_t)31; }
 int64_t msgwam_host_stage_doubles(int64_t n, int32_t G)
 {
     if (n < 0 || G < 3) return 0;
-    // 10 uploaded ray fields + ff + pkl + rr_out + mm_out, then grid (G+1), grids, rhobar, pg (2G), uu, vv, uu_out, vv_out
-    return 14 * pad32(n) + pad32(G + 1) + 8 * pad32(G);
+    // 10 uploaded ray fields + ff + pkl + rr_out + mm_out + 3 of stage-1 hand-over, then grid (G+1), grids, rhobar,
+    // pg (2G), uu, vv, uu_out, vv_out
+    return 17 * pad32(n) + pad32(G + 1) + 8 * pad32(G);
 }
 
 int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *const h_state[9], const double *h_dkk,
@@ -49,8 +50,8 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
     // state order: dens, lam, phi, rr, drr, kk, ll, mm, dmm  (lam is not needed on the device)
     double *d_dens = d, *d_phi = d + np, *d_rr = d + 2 * np, *d_drr = d + 3 * np, *d_kk = d + 4 * np, *d_ll = d + 5 * np,
            *d_mm = d + 6 * np, *d_dmm = d + 7 * np, *d_dkk = d + 8 * np, *d_dll = d + 9 * np, *d_ff = d + 10 * np,
-           *d_pkl = d + 11 * np, *d_rro = d + 12 * np, *d_mmo = d + 13 * np;
-    double *g = d + 14 * np;
+           *d_pkl = d + 11 * np, *d_rro = d + 12 * np, *d_mmo = d + 13 * np, *d_st1 = d + 14 * np;
+    double *g = d + 17 * np;
     double *d_grid = g, *d_grids = g + pad32(G + 1), *d_rho = d_grids + gp, *d_pg = d_rho + gp, *d_uu = d_pg + 2 * gp,
            *d_vv = d_uu + gp, *d_uuo = d_vv + gp, *d_vvo = d_uuo + gp;
     cudaError_t e;
@@ -73,7 +74,7 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
 #undef MW_H2D
     msgwam_rays_t r{};
     r.dens = d_dens; r.phi = d_phi; r.rr = d_rr; r.drr = d_drr; r.kk = d_kk; r.ll = d_ll; r.mm = d_mm; r.dmm = d_dmm;
-    r.dkk = d_dkk; r.dll = d_dll; r.ff = d_ff; r.pkl = d_pkl;
+    r.dkk = d_dkk; r.dll = d_dll; r.ff = d_ff; r.pkl = d_pkl; r.stage1 = d_st1;
     msgwam_grid_t gr{d_grid, d_grids, d_rho, d_pg, nullptr};
     rc = msgwam_column_step(p, &r, n, &gr, d_uu, d_vv, d_work, d_rro, d_mmo, d_uuo, d_vvo, stream);
     if (rc) return rc;

@@ -30,7 +30,7 @@ class Params(ctypes.Structure):
     ]
 
 
-_RAY_FIELDS = ("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm", "dkk", "dll", "rr_mm_area", "ff", "pkl")
+_RAY_FIELDS = ("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm", "dkk", "dll", "rr_mm_area", "ff", "pkl", "stage1")
 
 
 class Rays(ctypes.Structure):
@@ -86,7 +86,7 @@ SIGNATURES = {
 }
 
 
-ABI_VERSION = 2          # MSGWAM_ABI_VERSION of include/msgwam_b200.h
+ABI_VERSION = 3          # MSGWAM_ABI_VERSION of include/msgwam_b200.h
 
 
 def _load():

@@ -42,6 +42,7 @@ class Engine:
         self._stage = {}
         self._grid_cache = {}
         self._derived = None
+        self._scratch = None
         self.launches = 0          # kernels launched through this engine (bench.py reports it)
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -87,6 +88,13 @@ class Engine:
             w = self.zeros(int(lib.msgwam_column_work_doubles(G)))
             self._work[G] = w
         return w
+
+    def ray_scratch(self, n: int):
+        """3 n doubles for the stage-1 hand-over between the two sweeps (msgwam_rays_t.stage1)."""
+        t = self._scratch
+        if t is None or t.numel() < 3 * n:
+            t = self._scratch = self.empty(max(3 * n, 1))
+        return t
 
     def host_stage(self, n: int, G: int):
         key = (n, G)
@@ -144,6 +152,7 @@ class Engine:
         for k, t in (("dens", dens), ("phi", phi), ("rr", rr), ("drr", drr), ("kk", kk), ("ll", ll), ("mm", mm),
                      ("dmm", dmm), ("dkk", dkk), ("dll", dll), ("ff", ff), ("pkl", pkl)):
             setattr(rays, k, t.data_ptr())
+        rays.stage1 = self.ray_scratch(n).data_ptr()
         g = self.grid_struct(grid_devs)
         work = self.column_work(p.G)
         rr_out = self.empty(n) if rr_out is None else rr_out

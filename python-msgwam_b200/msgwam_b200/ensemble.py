@@ -44,6 +44,7 @@ class RayEnsemble:
         # one slab per buffer so that compaction can ping-pong between two of them
         self._slab = eng.empty(len(STATE) + len(STATICS) + 2, self.cap)
         self._slab2 = None
+        self._stage1 = None
         names = STATE + STATICS
         for i, (nm, a) in enumerate(zip(names, list(state) + [dkk, dll, rr_mm_area])):
             self._slab[i, :n].copy_(eng.dev(a, n))
@@ -90,6 +91,9 @@ class RayEnsemble:
         r = _cabi.Rays()
         for nm in STATE + STATICS + ("ff", "pkl"):
             setattr(r, nm, self.field(nm).data_ptr())
+        if self._stage1 is None or self._stage1.numel() < 3 * self.n:
+            self._stage1 = self.eng.empty(max(3 * self.cap, 1))     # stage-1 hand-over between the two sweeps
+        r.stage1 = self._stage1.data_ptr()
         return r
 
     def _reduce(self, t):

@@ -137,7 +137,7 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
         double2 *col = w.cell + (nlow - w.wb) * 32 + (threadIdx.x & 31);
         double t[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) t[k] = (nlow + k < nup) ? cell_weight(nlow + k, rl, ru, psv, dz, rdz, g) : 0.0;
+        for (int k = 0; k < 4; ++k) t[k] = cell_weight(min(nlow + k, nup - 1), rl, ru, psv, dz, rdz, g);   // clamped: no selects
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (nlow + k < nup) {

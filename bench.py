@@ -355,7 +355,8 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_steps / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1e6 ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000",
+        "config": {"workload": ("configs[1]: 1e6 ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000" if n == 1_000_000 else
+                                "configs[1] ensemble at %d ray volumes per GPU (--rays), 1-D column, constant N, zero mean wind, G=1000" % n),
                    "rays_per_gpu": n, "grid_levels": ens.G, "dt_s": sc.dt, "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": "rays sharded, %d rank(s); all-reduce of the deposited flux twice per step (%s)" % (
                        world, "none needed" if world == 1 else ("one-shot pushes over NVLink peer memory, fused into the tails of the two sweeps" if exchange is not None else "NCCL")),

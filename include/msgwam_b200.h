@@ -211,6 +211,19 @@ int msgwam_saturation(const msgwam_params_t *p, int64_t n, int32_t direct,
                       const double *d_grids, const double *d_rhobar, const double *d_bvf /* NULL or N on grids */,
                       double *d_out, void *stream);
 
+/* The driver's post-step clamp, /root/reference/raytracer.py:182-188: saturation(direct=True) on the propagated wave
+ * action with the step's finite-difference tendencies ((rr_new - rr_old) / 1 -- sic --, (drr_new - drr_old) / dt,
+ * (mm_new - mm_old) / dt), in one kernel, so that consecutive RK3 steps need not leave the device.  p->dt = dt.
+ * d_dens_out may alias d_dens. */
+int msgwam_saturation_step(const msgwam_params_t *p, int64_t n, const double *d_dens,
+                           const double *d_rr_old, const double *d_rr_new,
+                           const double *d_drr_old, const double *d_drr_new,
+                           const double *d_kk, const double *d_ll,
+                           const double *d_mm_old, const double *d_mm_new,
+                           const double *d_dkk, const double *d_dll, const double *d_area,
+                           const double *d_grids, const double *d_rhobar, const double *d_bvf /* NULL or N on grids */,
+                           double *d_dens_out, void *stream);
+
 /* ---- point functions (replace omega L:369, cg_rr L:434, cg_lambda L:386, cg_phi L:410,
  *      dk_dt L:451, dl_dt L:474, dm_dt L:502, gradients L:328) ------------------------------
  * op selects the function; unused inputs may be NULL.  For MSGWAM_OP_OMEGA_F the latitude is the

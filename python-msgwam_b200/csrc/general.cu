@@ -300,6 +300,30 @@ __global__ void __launch_bounds__(NT) saturation_kernel(const SatArgs a)
     }
 }
 
+// ---- the driver's post-step clamp (R:182-188): saturation(dt, dens_prop, rr_old, (rr_new - rr_old) / 1, drr_old,
+// (drr_new - drr_old) / dt, kk_new, ll_new, mm_old, (mm_new - mm_old) / dt, direct=True) -- bug for bug, including
+// the `/ 1` of the position increment.  One kernel between two RK3 steps keeps a whole run on the device.
+struct SatStepArgs {
+    msgwam_params_t p;
+    int64_t n;
+    const double *dens, *rr0, *rr1, *drr0, *drr1, *kk, *ll, *mm0, *mm1, *dkk, *dll, *area, *grids, *rhobar, *bvf;
+    double *out;
+};
+
+__global__ void __launch_bounds__(NT) saturation_step_kernel(const SatStepArgs a)
+{
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * NT) {
+        const double dens = a.dens[i], rr0 = a.rr0[i], drr0 = a.drr0[i], mm0 = a.mm0[i];
+        const double rr_st = dvd(sub(a.rr1[i], rr0), 1.0);                       // R:184 (`/ 1`, not `/ dt`)
+        const double drr_st = dvd(sub(a.drr1[i], drr0), a.p.dt);                 // R:185
+        const double mm_st = dvd(sub(a.mm1[i], mm0), a.p.dt);                    // R:187
+        double maxd;
+        const bool hit = saturation_limit(a.p, a.p.dt, dens, rr0, rr_st, drr0, drr_st, a.kk[i], a.ll[i], mm0, mm_st,
+                                          a.dkk[i], a.dll[i], a.area[i], a.grids, a.rhobar, a.bvf, maxd);
+        a.out[i] = hit ? maxd : dens;                                            // L:606-610
+    }
+}
+
 // ---- point functions ----------------------------------------------------------------------------
 struct PwArgs {
     msgwam_params_t p;
@@ -526,6 +550,25 @@ int msgwam_saturation(const msgwam_params_t *p, int64_t n, int32_t direct, const
     SatArgs a{*p, n, direct, d_dens, d_rr, d_rr_st, d_drr, d_drr_st, d_kk, d_ll, d_mm, d_mm_st, d_dkk, d_dll, d_area,
               d_grids, d_rhobar, d_bvf, d_out};
     saturation_kernel<<<grid_for(n, NT, 8), NT, 0, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int msgwam_saturation_step(const msgwam_params_t *p, int64_t n, const double *d_dens, const double *d_rr_old,
+                           const double *d_rr_new, const double *d_drr_old, const double *d_drr_new, const double *d_kk,
+                           const double *d_ll, const double *d_mm_old, const double *d_mm_new, const double *d_dkk,
+                           const double *d_dll, const double *d_area, const double *d_grids, const double *d_rhobar,
+                           const double *d_bvf, double *d_dens_out, void *stream)
+{
+    if (!p || n < 0) return MSGWAM_E_BADARG;
+    if (n == 0) return 0;
+    if (!d_dens || !d_rr_old || !d_rr_new || !d_drr_old || !d_drr_new || !d_kk || !d_ll || !d_mm_old || !d_mm_new || !d_dkk ||
+        !d_dll || !d_area || !d_grids || !d_rhobar || !d_dens_out)
+        return MSGWAM_E_BADARG;
+    int rc = props();
+    if (rc) return rc;
+    SatStepArgs a{*p, n, d_dens, d_rr_old, d_rr_new, d_drr_old, d_drr_new, d_kk, d_ll, d_mm_old, d_mm_new, d_dkk, d_dll,
+                  d_area, d_grids, d_rhobar, d_bvf, d_dens_out};
+    saturation_step_kernel<<<grid_for(n, NT, 8), NT, 0, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

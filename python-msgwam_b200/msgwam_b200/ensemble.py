@@ -45,6 +45,8 @@ class RayEnsemble:
         self._slab = eng.empty(len(STATE) + len(STATICS) + 2, self.cap)
         self._slab2 = None
         self._stage1 = None
+        self._old = None            # rr, drr, mm before a step (the post-step clamp needs both ends)
+        self.steps_done = 0
         names = STATE + STATICS
         for i, (nm, a) in enumerate(zip(names, list(state) + [dkk, dll, rr_mm_area])):
             self._slab[i, :n].copy_(eng.dev(a, n))
@@ -142,6 +144,38 @@ class RayEnsemble:
                 self.uu, self.vv = uu, vv
                 self._derive()
 
+    # ---- the driver's loop on the device ------------------------------------------------------------
+    def advance(self, dt, nsteps, saturate=True, history=None):
+        """The reference driver's time loop (raytracer.py:157-188) without leaving the device: nsteps times
+        RK3, then -- unless online saturation is on (R:182) -- the post-step clamp saturation(direct=True)
+        on the propagated wave action (one kernel, msgwam_saturation_step).  `history` (a History) receives
+        strided snapshots in place of the driver's (nt_max + 1, n) host arrays (R:125-136, 178-180)."""
+        eng = self.eng
+        p = self.params(dt)
+        clamp = saturate and not p.saturate_online
+        if history is not None and history.count == 0:
+            history.record(self, 0)
+        for k in range(1, nsteps + 1):
+            if clamp:
+                if self._old is None or self._old.shape[1] < self.cap:
+                    self._old = eng.empty(3, self.cap)
+                old = self._old[:, :self.n]
+                old[0].copy_(self.field("rr")); old[1].copy_(self.field("drr")); old[2].copy_(self.field("mm"))
+            self.step(dt)
+            if clamp:
+                dens = self.field("dens")
+                gd = self.grid_devs
+                check(lib.msgwam_saturation_step(
+                    p, self.n, eng.ptr(dens), eng.ptr(old[0]), eng.ptr(self.field("rr")), eng.ptr(old[1]),
+                    eng.ptr(self.field("drr")), eng.ptr(self.field("kk")), eng.ptr(self.field("ll")), eng.ptr(old[2]),
+                    eng.ptr(self.field("mm")), eng.ptr(self.field("dkk")), eng.ptr(self.field("dll")),
+                    eng.ptr(self.field("rr_mm_area")), eng.ptr(gd[1]), eng.ptr(gd[2]),
+                    eng.ptr(gd[4]) if len(gd) > 4 else _vp(0), eng.ptr(dens), eng.stream), "msgwam_saturation_step")
+                eng.launches += 1
+            self.steps_done += 1
+            if history is not None and self.steps_done % history.every == 0:
+                history.record(self, self.steps_done)
+
     # ---- deletion ---------------------------------------------------------------------------------
     def compact(self, dt=0.0, m_crit=float("inf")) -> int:
         """Delete rays outside the deposit domain (L:129-130) or with |m| >= m_crit.  Returns survivors."""
@@ -181,4 +215,33 @@ class RayEnsemble:
         for i, nm in enumerate(STATE):
             out[i] = self.field(nm).cpu().numpy()
         out[9], out[10] = self.uu.cpu().numpy(), self.vv.cpu().numpy()
+        return out
+
+
+class History:
+    """Device-side history of an ensemble run: what the reference driver keeps in (nt_max + 1, n) host arrays
+    (raytracer.py:125-136), as strided snapshots in HBM.  Fields: any of the ensemble's per-ray fields plus
+    'uu', 'vv'.  `to_host()` returns numpy arrays of shape (snapshots, n) / (snapshots, G) and the step numbers."""
+
+    def __init__(self, ens: RayEnsemble, nsnap: int, every: int = 1, fields=("dens", "rr", "drr", "mm", "dmm", "uu", "vv")):
+        self.every = max(int(every), 1)
+        self.fields = tuple(fields)
+        self.count = 0
+        self.steps = []
+        eng = ens.eng
+        self.buf = {f: eng.empty(nsnap, ens.G if f in ("uu", "vv") else ens.n) for f in self.fields}
+        self.nsnap = nsnap
+
+    def record(self, ens: RayEnsemble, step: int) -> None:
+        if self.count >= self.nsnap:
+            raise IndexError("History is full (%d snapshots)" % self.nsnap)
+        for f in self.fields:
+            src = ens.uu if f == "uu" else ens.vv if f == "vv" else ens.field(f)
+            self.buf[f][self.count, :src.numel()].copy_(src)
+        self.steps.append(int(step))
+        self.count += 1
+
+    def to_host(self):
+        out = {f: self.buf[f][:self.count].cpu().numpy() for f in self.fields}
+        out["steps"] = np.asarray(self.steps)
         return out

@@ -138,3 +138,57 @@ def test_critical_level_run_with_periodic_deletion():
         for i, nm in enumerate(STATE):
             assert np.array_equal(ens.field(nm).cpu().numpy(), np.asarray(got[i])[keep]), (cycle, nm)
     assert deleted > 0 and ens.n > 0
+
+
+def test_driver_loop_on_the_device_vs_reference_history():
+    """RayEnsemble.advance = raytracer.py's loop (R:157-188: RK3, then saturation(direct=True)) without leaving the
+    device, with a device-side history; compared with the history the unmodified driver produced (golden fixture)."""
+    from conftest import load_golden
+    from helpers import field_rel, max_rel
+    from msgwam_b200.ensemble import History, RayEnsemble
+    d = load_golden("driver_history.npz")
+    sc = scenarios.default_column()
+    ens = RayEnsemble.from_scenario(sc)
+    hist = History(ens, nsnap=400, every=1)
+    ens.advance(sc.dt, 360, saturate=True, history=hist)
+    h = hist.to_host()
+    assert list(h["steps"]) == list(range(361))
+    steps = list(d["steps"])
+    for nt in (0, 1, 2, 10, 100, 360):
+        k = steps.index(nt)
+        tol = 1e-13 if nt <= 10 else 1e-10
+        for nm in ("dens", "rr", "mm", "drr", "dmm"):
+            assert max_rel(h[nm][nt], d[nm][k]) <= tol, (nt, nm, max_rel(h[nm][nt], d[nm][k]))
+        assert field_rel(h["uu"][nt], d["uu"][k]) <= max(tol, 1e-12), nt
+    # advance(saturate=False) is plain stepping
+    a, b = RayEnsemble.from_scenario(sc), RayEnsemble.from_scenario(sc)
+    a.advance(sc.dt, 5, saturate=False); b.step(sc.dt, 5)
+    for nm in ("rr", "mm", "dens"):
+        assert np.array_equal(a.field(nm).cpu().numpy(), b.field(nm).cpu().numpy())
+
+
+@pytest.mark.parametrize("amplitude,steps,tol", [(8.0, 1, 2e-12), (1.0, 3, 1e-10)])
+def test_post_step_clamp_when_the_packet_saturates(amplitude, steps, tol):
+    """The driver's packet never reaches saturation, so the clamp is exercised here: ensembles at and far above the
+    static-instability amplitude, driver loop on the device vs the same loop through the oracle (R:157-188).  At eight
+    times the threshold two thirds of the rays are clamped and the flow is violently unstable (wavenumbers change sign
+    within a step; any 1e-16 difference grows ~1e3-fold per step, in the host-call loop just the same), hence one step."""
+    from helpers import max_rel
+    from msgwam_b200.ensemble import RayEnsemble
+    sc = scenarios.column_ensemble(30011, seed=41, ngrid=401, sheared=True, amplitude=amplitude)
+    ens = RayEnsemble.from_scenario(sc)
+    orc = oracle.Oracle(sc.oracle_cfg())
+    var = sc.var()
+    clamped = 0
+    for _ in range(steps):
+        out = orc.RK3(sc.dt, var)
+        dens = orc.saturation(sc.dt, out[0], var[3], (out[3] - var[3]) / 1, var[4], (out[4] - var[4]) / sc.dt, out[5], out[6],
+                              var[7], (out[7] - var[7]) / sc.dt, direct=True)
+        clamped += int(np.count_nonzero(dens != out[0]))
+        out[0] = dens
+        var = out
+    assert clamped > (1000 if amplitude > 2 else 0), clamped
+    ens.advance(sc.dt, steps, saturate=True)
+    got = ens.to_var()
+    assert max_rel(got[0], var[0]) <= tol
+    close(got, var, sc.var(), ray_tol=tol, grid_tol=10 * tol)

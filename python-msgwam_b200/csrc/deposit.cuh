@@ -90,14 +90,23 @@ __device__ __forceinline__ double cell_weight(int c, double rl, double ru, doubl
 // Overlap weights of one ray volume [rl, ru] with cells [nlow, nup) times (psv * v0, psv * v1),
 // L:156-163:  w = |min(grid[c+1], ru) - max(grid[c], rl)| / dz;  out[c] += w * psv * v.
 // `ok` is false for lanes without a ray or with an out-of-domain ray; all 32 lanes must call.
-// h0/h1: where window flushes go (the global deposit in the sweeps); s0/s1 + used: the CTA histogram for
-// scattered warps and its "dirty" flag (pass s0 = h0, s1 = h1, used = nullptr to add there directly).
-template <int WIN>
+// h0/h1: where window flushes go (the global deposit in the sweeps); sink: where outlier lanes add (see above).
+// Outlier sinks: where a lane that does not fit its warp's window adds (cell, x, y): two arrays (a CTA histogram in
+// shared memory, or the output itself), one fp64 atomicAdd each; `used`, if given, marks the histogram dirty for the
+// merge at the end of the CTA.  (Measured and rejected: both components side by side with ONE 128-bit
+// compare-and-swap per cell, ATOMS.CAS.128 -- 2-3x slower than two 64-bit CAS loops; fp64 RED straight to the global
+// deposit -- 2.5x slower once the rays are dispersed, 6x for unordered rays.)
+struct SplitTargets {
+    double *s0, *s1; int *used;
+    __device__ __forceinline__ void mark() const { if (used != nullptr) *used = 1; }
+    __device__ __forceinline__ void add(int c, double x, double y) const { atomicAdd(s0 + c, x); atomicAdd(s1 + c, y); }
+};
+
+template <int WIN, class Sink>
 __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double rl, double ru,
                                               double psv, double v0, double v1,
                                               double dz, double rdz, const double *__restrict__ g,
-                                              WindowT<WIN> &w, double *h0, double *h1,
-                                              double *s0, double *s1, int *used)
+                                              WindowT<WIN> &w, double *h0, double *h1, const Sink &sink)
 {
     ok = ok && (nup > nlow);
     const int lo = __reduce_min_sync(FULL_MASK, ok ? nlow : INT_MAX);
@@ -154,11 +163,10 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
         }
     } else if (ok) {
         // outlier lane / unordered rays: add to the CTA histogram directly
-        if (used != nullptr) *used = 1;
+        sink.mark();
         for (int c = nlow; c < nup; ++c) {
             const double tc = cell_weight(c, rl, ru, psv, dz, rdz, g);
-            atomicAdd(s0 + c, mul(tc, v0));
-            atomicAdd(s1 + c, mul(tc, v1));
+            sink.add(c, mul(tc, v0), mul(tc, v1));
         }
     }
 }

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NT) project_kernel(const ProjArgs a)
                 }
             }
         }
-        deposit_cells(ok, nlow, nup, rl, ru, psv, v0, v1, a.dz, a.rdz, g, win, h0, h1, h0, h1, (int *)nullptr);
+        deposit_cells(ok, nlow, nup, rl, ru, psv, v0, v1, a.dz, a.rdz, g, win, h0, h1, SplitTargets{h0, h1, nullptr});
     }
     window_flush(win, h0, h1);
     if (a.use_smem) {

@@ -187,6 +187,19 @@ int msgwam_mean_flow_tendency(int32_t which, double f0, int32_t G, const double 
 int msgwam_rk_update(int32_t stage, double dt, const double *d_tend, double *d_q,
                      const double *d_x, double *d_x_out, int64_t n, void *stream);
 
+/* ---- one fused RK stage for any mode (HPROP on/off, saturate_online on/off, N(z) profile) --------------------
+ * msgwam_rk_stage_rays: rhs_default on the state in `rays` (L:618-651), its deposit wave_projection(var=0) of the same
+ * state (L:653-658, accumulated into d_proj, which must be zero on entry) and the low-storage update of the nine ray
+ * slots (L:693-698: stage 0: q = dt*k, x += q/3; stage 1, 2: q = dt*k - a*q, x += b*q) in one sweep.  d_x_out[f] may
+ * alias the state in `rays`.  [multi-GPU: all-reduce d_proj here]  msgwam_rk_stage_grid: du_st, dv_st from the deposit
+ * (L:659-666), the same update for uu, vv, and d_proj zeroed for the next stage.  Three such pairs are one RK3. */
+int msgwam_rk_stage_rays(int32_t stage, const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                         const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
+                         double *const d_q[9], double *const d_x_out[9], double *d_proj, void *stream);
+int msgwam_rk_stage_grid(int32_t stage, const msgwam_params_t *p, const msgwam_grid_t *grid,
+                         const double *d_uu, const double *d_vv, double *d_proj,
+                         double *d_qu, double *d_qv, double *d_uu_out, double *d_vv_out, void *stream);
+
 /* ---- deposition  (replaces wave_projection L:92-221, var = 0..4, any uniform grid) ----------
  * out sizes: var 0 -> 2*(ng-1); 1,2 -> ng-1; 3 -> ng; 4 -> 2*ng doubles, zeroed by the call.
  * dz = np.diff(grid[:2])[0] of the grid passed (L:123) and inv_dz = 1.0/dz, derived by the host. */

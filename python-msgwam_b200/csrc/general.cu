@@ -64,73 +64,83 @@ __device__ __forceinline__ bool saturation_limit(const msgwam_params_t &p, doubl
     return maxd < mul(dens, psv);
 }
 
-// rhs_default's nine ray tendencies (L:629-651), all branches
-__global__ void __launch_bounds__(NT) rhs_rays_kernel(const RhsArgs a)
+// rhs_default's nine ray tendencies (L:629-651), all branches, for ray i: x[9] receives the state, t[9] the tendencies
+__device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9], double t[9])
 {
     const msgwam_params_t &p = a.p;
     const int G = p.G;
+    const double lam = a.r.lam ? a.r.lam[i] : 0.0;
+    const double dens = a.r.dens[i], phi = a.r.phi[i], rr = a.r.rr[i], drr = a.r.drr[i];
+    const double kk = a.r.kk[i], ll = a.r.ll[i], mm = a.r.mm[i], dmm = a.r.dmm[i];
+    const double sphi = sin(phi), cphi = cos(phi);
+    const double ff = mul(p.two_rot, sphi), f2 = mul(ff, ff);
+    const double kh2 = add(mul(kk, kk), mul(ll, ll)), m2 = mul(mm, mm);
+    const double vk = add(kh2, m2);
+    const double n2 = n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, rr);     // ext: N^2 at the ray centre
+    const double om = omega_from(kh2, m2, f2, n2);
+    const double cgr = dvd(dvd(mul(-mm, sub(mul(om, om), f2)), om), vk);      // L:448 (at the centre)
+    double cgr_up = cgr, cgr_down = cgr;                                      // cg_rr ignores rr: up == down (L:635-636)
+    if (a.bvf != nullptr) {                                                   // ext: N at the two edges
+        const double hd = mul(.5, drr);
+        cgr_up = cg_rr_from(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, add(rr, hd)));
+        cgr_down = cg_rr_from(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, sub(rr, hd)));
+    }
+    double du_ray, dv_ray;
+    shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
+    double cgl = 0.0, cgp = 0.0;
+    if (p.hprop) {                                                            // L:400-405, 424-429
+        const double uu_ray = interp1(rr, a.grids, a.uu, G, p.inv_dz_grids);
+        const double vv_ray = interp1(rr, a.grids, a.vv, G, p.inv_dz_grids);
+        const double nd = sub(n2, mul(om, om));
+        cgl = add(mul(dvd(dvd(kk, om), vk), nd), uu_ray);
+        cgp = add(mul(dvd(dvd(ll, om), vk), nd), vv_ray);
+    }
+    const double rad = add(p.rad_earth, rr);
+    const double drr_st = mul(.5, add(cgr_down, cgr_up));                     // L:640
+    const double ddrr_st = sub(cgr_up, cgr_down);                             // L:641
+    double dkk_st = 0.0, dll_st = 0.0;
+    if (p.hprop) {
+        const double tphi = tan(phi);
+        const double zero = add(mul(kk, 0.0), mul(ll, 0.0));
+        const double g_lam = dvd(dvd(zero, rad), cphi);                       // L:465
+        dkk_st = sub(mul(dvd(kk, rad), sub(mul(tphi, cgp), cgr)), g_lam);     // L:468-469
+        const double g_phi = dvd(zero, rad);                                  // L:489
+        const double df2 = mul(mul(mul(p.c8rot2, sphi), cphi), 1.0);          // L:491
+        const double t3 = mul(dvd(dvd(dvd(m2, 2.0), om), vk), df2);
+        const double sum = add(add(mul(ll, cgr), mul(mul(kk, tphi), cgl)), t3);
+        dll_st = sub(dvd(-sum, rad), g_phi);                                  // L:494-497
+    }
+    const double g_rr = add(mul(kk, du_ray), mul(ll, dv_ray));                // L:517
+    double dmm_st = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), g_rr);     // L:519-520
+    if (a.bvf != nullptr) {                                                   // ext: - N N' (k^2 + l^2) / om / |k|^2
+        const double nr = interp1(rr, a.grids, a.bvf, G, p.inv_dz_grids);
+        double dnr, unused;
+        shear_interp(rr, a.grid, a.bvf, a.bvf, G, p.dz_grid, p.inv_dz_grid, dnr, unused);
+        dmm_st = sub(dmm_st, dvd(dvd(mul(mul(nr, dnr), kh2), om), vk));
+    }
+    double maxd;
+    const bool hit = saturation_limit(p, p.dt, dens, rr, drr_st, drr, ddrr_st, kk, ll, mm, dmm_st,
+                                      a.r.dkk[i], a.r.dll[i], a.r.rr_mm_area[i], a.grids, a.rhobar, a.bvf, maxd);
+    const double st = hit ? dvd(sub(maxd, dens), p.dt) : 0.0;                 // L:612-615
+    x[0] = dens; x[1] = lam; x[2] = phi; x[3] = rr; x[4] = drr; x[5] = kk; x[6] = ll; x[7] = mm; x[8] = dmm;
+    t[0] = mul(p.saturate_online ? 1.0 : 0.0, st);                            // L:647
+    t[1] = dvd(dvd(cgl, rad), cphi);                                          // L:638
+    t[2] = dvd(cgp, rad);                                                     // L:639
+    t[3] = drr_st;
+    t[4] = ddrr_st;
+    t[5] = dkk_st;
+    t[6] = dll_st;
+    t[7] = dmm_st;
+    t[8] = mul(dvd(dmm, drr), ddrr_st);                                       // L:645
+}
+
+__global__ void __launch_bounds__(NT) rhs_rays_kernel(const RhsArgs a)
+{
     for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * NT) {
-        const double dens = a.r.dens[i], phi = a.r.phi[i], rr = a.r.rr[i], drr = a.r.drr[i];
-        const double kk = a.r.kk[i], ll = a.r.ll[i], mm = a.r.mm[i], dmm = a.r.dmm[i];
-        const double sphi = sin(phi), cphi = cos(phi);
-        const double ff = mul(p.two_rot, sphi), f2 = mul(ff, ff);
-        const double kh2 = add(mul(kk, kk), mul(ll, ll)), m2 = mul(mm, mm);
-        const double vk = add(kh2, m2);
-        const double n2 = n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, rr);     // ext: N^2 at the ray centre
-        const double om = omega_from(kh2, m2, f2, n2);
-        const double cgr = dvd(dvd(mul(-mm, sub(mul(om, om), f2)), om), vk);      // L:448 (at the centre)
-        double cgr_up = cgr, cgr_down = cgr;                                      // cg_rr ignores rr: up == down (L:635-636)
-        if (a.bvf != nullptr) {                                                   // ext: N at the two edges
-            const double hd = mul(.5, drr);
-            cgr_up = cg_rr_from(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, add(rr, hd)));
-            cgr_down = cg_rr_from(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, sub(rr, hd)));
-        }
-        double du_ray, dv_ray;
-        shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
-        double cgl = 0.0, cgp = 0.0;
-        if (p.hprop) {                                                            // L:400-405, 424-429
-            const double uu_ray = interp1(rr, a.grids, a.uu, G, p.inv_dz_grids);
-            const double vv_ray = interp1(rr, a.grids, a.vv, G, p.inv_dz_grids);
-            const double nd = sub(n2, mul(om, om));
-            cgl = add(mul(dvd(dvd(kk, om), vk), nd), uu_ray);
-            cgp = add(mul(dvd(dvd(ll, om), vk), nd), vv_ray);
-        }
-        const double rad = add(p.rad_earth, rr);
-        const double drr_st = mul(.5, add(cgr_down, cgr_up));                     // L:640
-        const double ddrr_st = sub(cgr_up, cgr_down);                             // L:641
-        double dkk_st = 0.0, dll_st = 0.0;
-        if (p.hprop) {
-            const double tphi = tan(phi);
-            const double zero = add(mul(kk, 0.0), mul(ll, 0.0));
-            const double g_lam = dvd(dvd(zero, rad), cphi);                       // L:465
-            dkk_st = sub(mul(dvd(kk, rad), sub(mul(tphi, cgp), cgr)), g_lam);     // L:468-469
-            const double g_phi = dvd(zero, rad);                                  // L:489
-            const double df2 = mul(mul(mul(p.c8rot2, sphi), cphi), 1.0);          // L:491
-            const double t3 = mul(dvd(dvd(dvd(m2, 2.0), om), vk), df2);
-            const double sum = add(add(mul(ll, cgr), mul(mul(kk, tphi), cgl)), t3);
-            dll_st = sub(dvd(-sum, rad), g_phi);                                  // L:494-497
-        }
-        const double g_rr = add(mul(kk, du_ray), mul(ll, dv_ray));                // L:517
-        double dmm_st = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), g_rr);     // L:519-520
-        if (a.bvf != nullptr) {                                                   // ext: - N N' (k^2 + l^2) / om / |k|^2
-            const double nr = interp1(rr, a.grids, a.bvf, G, p.inv_dz_grids);
-            double dnr, unused;
-            shear_interp(rr, a.grid, a.bvf, a.bvf, G, p.dz_grid, p.inv_dz_grid, dnr, unused);
-            dmm_st = sub(dmm_st, dvd(dvd(mul(mul(nr, dnr), kh2), om), vk));
-        }
-        double maxd;
-        const bool hit = saturation_limit(p, p.dt, dens, rr, drr_st, drr, ddrr_st, kk, ll, mm, dmm_st,
-                                          a.r.dkk[i], a.r.dll[i], a.r.rr_mm_area[i], a.grids, a.rhobar, a.bvf, maxd);
-        const double st = hit ? dvd(sub(maxd, dens), p.dt) : 0.0;                 // L:612-615
-        a.tend[0][i] = mul(p.saturate_online ? 1.0 : 0.0, st);                    // L:647
-        a.tend[1][i] = dvd(dvd(cgl, rad), cphi);                                  // L:638
-        a.tend[2][i] = dvd(cgp, rad);                                             // L:639
-        a.tend[3][i] = drr_st;
-        a.tend[4][i] = ddrr_st;
-        a.tend[5][i] = dkk_st;
-        a.tend[6][i] = dll_st;
-        a.tend[7][i] = dmm_st;
-        a.tend[8][i] = mul(dvd(dmm, drr), ddrr_st);                               // L:645
+        double x[9], t[9];
+        ray_rhs(a, i, x, t);
+#pragma unroll
+        for (int f = 0; f < 9; ++f) a.tend[f][i] = t[f];
     }
 }
 
@@ -278,6 +288,116 @@ __global__ void rk_update_kernel(int stage, double dt, const double *__restrict_
             q[i] = qq; xo[i] = add(x[i], mul(bs, qq));
         }
     }
+}
+
+// ---- one fused RK stage for any mode (HPROP, online saturation, N(z) profile) ------------------------------
+// rhs_default on state x_s (ray_rhs), its deposit (wave_projection var = 0 of the same state, L:653-658) and the
+// low-storage update of all nine ray slots (L:693-698) in one sweep: 9 + 3 + 9 fields read, 9 + 9 written, instead
+// of the rhs / projection / 9 x rk_update kernels (~1.9 KB/ray-step of traffic and ~45 launches per step).
+struct StageArgs {
+    RhsArgs r;                  // state in, statics, grid fields, uu_s, vv_s
+    int stage;
+    double *q[9];               // low-storage register, in/out (written only at stage 0)
+    double *xo[9];              // state out (may alias the state in)
+    double *proj;               // (2, G-1) deposit, accumulated (zero on entry)
+    int use_smem;
+};
+
+// dynamic shared memory: warp windows | grids copy | CTA histogram (when they fit), as in project_kernel
+__global__ void __launch_bounds__(NT) stage_rays_kernel(const StageArgs a)
+{
+    extern __shared__ double sm[];
+    const msgwam_params_t &p = a.r.p;
+    const int ng = p.G, nc = ng - 1;
+    double *wins = sm + ((reinterpret_cast<uintptr_t>(sm) & 8) ? 1 : 0);
+    double *rest = wins + (NT / 32) * WIN_DOUBLES;
+    double *h0, *h1;
+    const double *g;
+    Window win;
+    window_init(win, wins + (size_t)(threadIdx.x >> 5) * WIN_DOUBLES);
+    if (a.use_smem) {
+        double *gsm = rest; h0 = rest + ng; h1 = h0 + nc;
+        for (int j = threadIdx.x; j < ng; j += NT) gsm[j] = a.r.grids[j];
+        for (int j = threadIdx.x; j < 2 * nc; j += NT) h0[j] = 0.0;
+        g = gsm;
+    } else { g = a.r.grids; h0 = a.proj; h1 = a.proj + nc; }
+    __syncthreads();
+    const double as = a.stage == 1 ? 5 / 9. : 153 / 128., bs = a.stage == 1 ? 15 / 16. : 8 / 15.;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (NT / 32);
+    const int64_t gw = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    const int64_t per = (((a.r.n + nwarps - 1) / nwarps) + 31) & ~(int64_t)31;
+    const int64_t begin = gw * per;
+    const int64_t end = (begin + per < a.r.n) ? begin + per : a.r.n;
+    for (int64_t base = begin; base < end; base += 32) {
+        const int64_t i = base + lane;
+        const bool live = i < end;
+        double rl = 0.0, ru = 0.0, psv = 0.0, v0 = 0.0, v1 = 0.0;
+        int nlow = 0, nup = 0;
+        bool ok = false;
+        double x[9], t[9];
+        if (live) {
+            ray_rhs(a.r, i, x, t);
+            // wave_projection(var = 0) of the same state, called as L:654-658
+            const double hd = mul(.5, x[4]), hm = mul(.5, x[8]);
+            rl = sub(x[3], hd); ru = add(x[3], hd);
+            const double ml = sub(x[7], hm), mu = add(x[7], hm);
+            ok = cell_range(rl, ru, p.dz_grids, p.inv_dz_grids, ng - 2, nlow, nup);
+            if (ok) {
+                psv = fabs(mul(mul(a.r.r.dkk[i], a.r.r.dll[i]), x[8]));           // L:137
+                const double ff = mul(p.two_rot, sin(x[2]));
+                const double n2 = n2_at(a.r.bvf, a.r.grids, ng, p.inv_dz_grids, p.n2, mul(.5, add(rl, ru)));
+                const double cgr = cg_rr_from(add(mul(x[5], x[5]), mul(x[6], x[6])), mul(.5, add(ml, mu)), mul(ff, ff), n2);
+                v0 = mul(mul(cgr, x[5]), x[0]); v1 = mul(mul(cgr, x[6]), x[0]);   // L:148-149
+            }
+        }
+        deposit_cells(ok, nlow, nup, rl, ru, psv, v0, v1, p.dz_grids, p.inv_dz_grids, g, win, h0, h1, SplitTargets{h0, h1, nullptr});
+        if (live) {
+#pragma unroll
+            for (int f = 0; f < 9; ++f) {                                         // L:693-698
+                double qq;
+                if (a.stage == 0) { qq = mul(p.dt, t[f]); a.xo[f][i] = add(x[f], dvd(qq, 3.0)); }
+                else { qq = sub(mul(p.dt, t[f]), mul(as, a.q[f][i])); a.xo[f][i] = add(x[f], mul(bs, qq)); }
+                a.q[f][i] = qq;
+            }
+        }
+    }
+    window_flush(win, h0, h1);
+    if (a.use_smem) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < 2 * nc; j += NT) {
+            const double v = h0[j];
+            if (v != 0.0) atomicAdd(a.proj + j, v);
+        }
+    }
+}
+
+// the mean-flow half of the stage: du_st, dv_st from the (reduced) deposit (L:653-666, 523-558), the low-storage
+// update of uu, vv, and the deposit zeroed for the next stage.  One CTA.
+__global__ void __launch_bounds__(1024) stage_grid_kernel(int stage, msgwam_params_t p, const double *__restrict__ rhobar,
+                                                          const double *__restrict__ pg, const double *uu, const double *vv,
+                                                          double *D, double *qu, double *qv, double *uo, double *vo)
+{
+    const int G = p.G, nc = G - 1;
+    const double as = stage == 1 ? 5 / 9. : 153 / 128., bs = stage == 1 ? 15 / 16. : 8 / 15.;
+    for (int j = threadIdx.x; j < G; j += blockDim.x) {
+        const int i0 = min(max(j - 1, 0), nc - 1), i1 = min(j, nc - 1);
+        const double g0 = dvd(sub(D[i1], D[i0]), p.dz_grid);
+        const double g1 = dvd(sub(D[nc + i1], D[nc + i0]), p.dz_grid);
+        const double rinv = dvd(1.0, rhobar[j]);
+        const double u = uu[j], v = vv[j];
+        const double du = sub(mul(p.f0, v), mul(rinv, add(pg[j], g0)));
+        const double dv = sub(mul(-p.f0, u), mul(rinv, add(pg[G + j], g1)));
+        double q0, q1;
+        if (stage == 0) { q0 = mul(p.dt, du); q1 = mul(p.dt, dv); uo[j] = add(u, dvd(q0, 3.0)); vo[j] = add(v, dvd(q1, 3.0)); }
+        else {
+            q0 = sub(mul(p.dt, du), mul(as, qu[j])); q1 = sub(mul(p.dt, dv), mul(as, qv[j]));
+            uo[j] = add(u, mul(bs, q0)); vo[j] = add(v, mul(bs, q1));
+        }
+        qu[j] = q0; qv[j] = q1;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * nc; j += blockDim.x) D[j] = 0.0;
 }
 
 // ---- saturation (L:561-615) ---------------------------------------------------------------------
@@ -468,6 +588,53 @@ int msgwam_rhs_rays(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t
         return launch_project(q, n, s);
     }
     return 0;
+}
+
+int msgwam_rk_stage_rays(int32_t stage, const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                         const msgwam_grid_t *grid, const double *d_uu, const double *d_vv, double *const d_q[9],
+                         double *const d_x_out[9], double *d_proj, void *stream)
+{
+    if (!p || !rays || !grid || !d_uu || !d_vv || !d_q || !d_x_out || !d_proj || n < 0 || stage < 0 || stage > 2)
+        return MSGWAM_E_BADARG;
+    if (p->G < 3) return MSGWAM_E_GRID_SIZE;
+    if (n == 0) return 0;
+    int rc = props();
+    if (rc) return rc;
+    if (!rays->dens || !rays->lam || !rays->phi || !rays->rr || !rays->drr || !rays->kk || !rays->ll || !rays->mm || !rays->dmm ||
+        !rays->dkk || !rays->dll || !rays->rr_mm_area || !grid->grid || !grid->grids || !grid->rhobar)
+        return MSGWAM_E_BADARG;
+    StageArgs a{};
+    a.r.p = *p; a.r.r = *rays; a.r.n = n;
+    a.r.grid = grid->grid; a.r.grids = grid->grids; a.r.rhobar = grid->rhobar; a.r.uu = d_uu; a.r.vv = d_vv; a.r.bvf = grid->bvf;
+    a.stage = stage; a.proj = d_proj;
+    for (int f = 0; f < 9; ++f) {
+        if (!d_q[f] || !d_x_out[f]) return MSGWAM_E_BADARG;
+        a.q[f] = d_q[f]; a.xo[f] = d_x_out[f];
+    }
+    const size_t win_bytes = ((size_t)(NT / 32) * WIN_DOUBLES + 2) * sizeof(double);
+    const size_t full = win_bytes + (size_t)(p->G + 2 * (p->G - 1)) * sizeof(double);
+    a.use_smem = full <= (size_t)g_smem;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(stage_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    stage_rays_kernel<<<grid_for(n, NT * 8, 2), NT, a.use_smem ? full : win_bytes, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int msgwam_rk_stage_grid(int32_t stage, const msgwam_params_t *p, const msgwam_grid_t *grid, const double *d_uu,
+                         const double *d_vv, double *d_proj, double *d_qu, double *d_qv, double *d_uu_out, double *d_vv_out,
+                         void *stream)
+{
+    if (!p || !grid || !d_uu || !d_vv || !d_proj || !d_qu || !d_qv || !d_uu_out || !d_vv_out || stage < 0 || stage > 2 ||
+        !grid->rhobar || !grid->pg)
+        return MSGWAM_E_BADARG;
+    if (p->G < 3) return MSGWAM_E_GRID_SIZE;
+    stage_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(stage, *p, grid->rhobar, grid->pg, d_uu, d_vv, d_proj, d_qu, d_qv,
+                                                           d_uu_out, d_vv_out);
+    return (int)cudaGetLastError();
 }
 
 int msgwam_grid_tendency(const msgwam_params_t *p, const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,

@@ -72,6 +72,8 @@ SIGNATURES = {
     "msgwam_column_step": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_debug_cg_rr_fast": (ctypes.c_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _i64, _vp]),
     "msgwam_rhs_rays": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp]),
+    "msgwam_rk_stage_rays": (ctypes.c_int, [_i32, _PP, _RP, _i64, _GP, _vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp]),
+    "msgwam_rk_stage_grid": (ctypes.c_int, [_i32, _PP, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_grid_tendency": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_mean_flow_tendency": (ctypes.c_int, [_i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_rk_update": (ctypes.c_int, [_i32, _dbl, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -203,24 +203,33 @@ class Engine:
         self.launches += 3
         return tend, du, dv, proj
 
-    def rk3_general(self, p: Params, state, statics, uu, vv, grid_devs, reduce_fn=None):
-        """RK3 with rhs_default for any mode: three stages of rhs_general + low-storage updates."""
-        x = list(state)
-        n = x[0].numel()
+    def rk3_general(self, p: Params, state, statics, uu, vv, grid_devs, reduce_fn=None, in_place=False):
+        """RK3 with rhs_default for any mode: per stage one fused ray sweep (rhs + deposit + low-storage update,
+        msgwam_rk_stage_rays), the all-reduce of the deposit when sharded, and the one-CTA mean-flow stage
+        (msgwam_rk_stage_grid) -- six launches per step.  in_place: overwrite `state` instead of allocating."""
+        n = state[0].numel()
+        x_in = list(state)
+        x_out = list(state) if in_place else [self.empty(n) for _ in range(9)]
         q = [self.empty(n) for _ in range(9)]
         qu, qv = self.empty(p.G), self.empty(p.G)
+        proj = self.zeros(2, p.G - 1)
+        g = self.grid_struct(grid_devs)
         s = self.stream
+        qp = (_vp * 9)(*[t.data_ptr() for t in q])
+        xop = (_vp * 9)(*[t.data_ptr() for t in x_out])
         for stage in range(3):
-            tend, du, dv, _ = self.rhs_general(p, x, statics, uu, vv, grid_devs, reduce_fn)
-            xn = []
-            for f in range(9):
-                o = self.empty(n)
-                check(lib.msgwam_rk_update(stage, p.dt, self.ptr(tend[f]), self.ptr(q[f]), self.ptr(x[f]), self.ptr(o), n, s),
-                      "msgwam_rk_update")
-                xn.append(o)
+            rays = Rays()
+            for k, t in zip(("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm"), x_in):
+                setattr(rays, k, t.data_ptr())
+            for k, t in zip(("dkk", "dll", "rr_mm_area"), statics):
+                setattr(rays, k, t.data_ptr())
+            check(lib.msgwam_rk_stage_rays(stage, p, rays, n, g, self.ptr(uu), self.ptr(vv), qp, xop, self.ptr(proj), s),
+                  "msgwam_rk_stage_rays")
+            if reduce_fn is not None:
+                reduce_fn(proj)
             un, vn = self.empty(p.G), self.empty(p.G)
-            check(lib.msgwam_rk_update(stage, p.dt, self.ptr(du), self.ptr(qu), self.ptr(uu), self.ptr(un), p.G, s), "msgwam_rk_update")
-            check(lib.msgwam_rk_update(stage, p.dt, self.ptr(dv), self.ptr(qv), self.ptr(vv), self.ptr(vn), p.G, s), "msgwam_rk_update")
-            self.launches += 11
-            x, uu, vv = xn, un, vn
-        return x, uu, vv
+            check(lib.msgwam_rk_stage_grid(stage, p, g, self.ptr(uu), self.ptr(vv), self.ptr(proj), self.ptr(qu), self.ptr(qv),
+                                           self.ptr(un), self.ptr(vn), s), "msgwam_rk_stage_grid")
+            self.launches += 2
+            x_in, uu, vv = x_out, un, vn
+        return x_out, uu, vv

@@ -153,11 +153,10 @@ class RayEnsemble:
             else:
                 state = [self.field(nm) for nm in STATE]
                 st = [self.field(nm) for nm in STATICS]
-                x, uu, vv = eng.rk3_general(p, state, st, self.uu, self.vv, self.grid_devs, self._reduce)
-                for nm, t in zip(STATE, x):
-                    self.field(nm).copy_(t)
+                x, uu, vv = eng.rk3_general(p, state, st, self.uu, self.vv, self.grid_devs, self._reduce, in_place=True)
                 self.uu, self.vv = uu, vv
-                self._derive()
+                if p.hprop:
+                    self._derive()                  # phi moved: ff = 2 Omega sin(phi) for the column kernels
 
     # ---- the driver's loop on the device ------------------------------------------------------------
     def advance(self, dt, nsteps, saturate=True, history=None):

@@ -304,7 +304,7 @@ struct StageArgs {
 };
 
 // dynamic shared memory: warp windows | grids copy | CTA histogram (when they fit), as in project_kernel
-__global__ void __launch_bounds__(NT) stage_rays_kernel(const StageArgs a)
+__global__ void __launch_bounds__(NT, 3) stage_rays_kernel(const StageArgs a)
 {
     extern __shared__ double sm[];
     const msgwam_params_t &p = a.r.p;
@@ -620,7 +620,7 @@ int msgwam_rk_stage_rays(int32_t stage, const msgwam_params_t *p, const msgwam_r
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    stage_rays_kernel<<<grid_for(n, NT * 8, 2), NT, a.use_smem ? full : win_bytes, (cudaStream_t)stream>>>(a);
+    stage_rays_kernel<<<grid_for(n, NT * 8, 3), NT, a.use_smem ? full : win_bytes, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

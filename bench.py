@@ -169,8 +169,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1e6 ray volumes, 1-D column, constant N, zero mean wind, G=1000", "rays": n,
-                   "grid_levels": 1000, "dt_s": sc.dt},
+        "config": {"workload": ("configs[1]: 1e6 ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000" if args.rays == 1_000_000 else
+                                "configs[1] ensemble at %d ray volumes per GPU (--rays), 1-D column, constant N, zero mean wind, G=1000" % args.rays),
+                   "rays_per_gpu": args.rays, "grid_levels": 1000, "dt_s": sc.dt,
+                   "sample": "each timed step advances a bounded sample of %d rays of that ensemble on the host cores" % n},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "oracle/msgwam_oracle.c (C restatement of lib/libprop.py RK3+rhs_default+wave_projection; the "
                                    "Python reference cannot run on the GPU box and does ~2.3e4 ray-steps/s, BASELINE.md) on %d rays per step, "

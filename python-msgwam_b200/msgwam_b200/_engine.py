@@ -43,6 +43,7 @@ class Engine:
         self._grid_cache = {}
         self._derived = None
         self._scratch = None
+        self._gmax = None
         self.launches = 0          # kernels launched through this engine (bench.py reports it)
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -88,6 +89,13 @@ class Engine:
             w = self.zeros(int(lib.msgwam_column_work_doubles(G)))
             self._work[G] = w
         return w
+
+    def column_max_levels(self) -> int:
+        """Largest G the fused column kernels take on this device (their shear tables live in shared memory);
+        taller grids run stage by stage through the general kernels."""
+        if self._gmax is None:
+            self._gmax = int(lib.msgwam_column_max_levels())
+        return self._gmax
 
     def ray_scratch(self, n: int):
         """3 n doubles for the stage-1 hand-over between the two sweeps (msgwam_rays_t.stage1)."""

@@ -122,7 +122,7 @@ class RayEnsemble:
         eng = self.eng
         p = self.params(dt)
         g = eng.grid_struct(self.grid_devs)
-        column = not p.hprop and not p.saturate_online and len(self.grid_devs) == 4
+        column = not p.hprop and not p.saturate_online and len(self.grid_devs) == 4 and self.G <= eng.column_max_levels()
         nc = self.G - 1
         if column:
             rays = self._rays()

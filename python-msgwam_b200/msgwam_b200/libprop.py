@@ -475,7 +475,7 @@ def RK3(dt, var):
     eng = _engine()
     p = _params(dt)
     like_dev = _any_dev(eng, *var)
-    column = not p.hprop and not p.saturate_online and _bvf_profile() is None
+    column = not p.hprop and not p.saturate_online and _bvf_profile() is None and p.G <= eng.column_max_levels()
     if column and not like_dev:
         return _rk3_numpy_column(eng, p, var)
     n = _size(var[3])

@@ -52,6 +52,17 @@ def test_largest_grid_the_column_kernels_take(lprop):
     run_both(lprop, sc, steps=2)
 
 
+def test_grid_taller_than_the_column_kernels_take_falls_back_to_the_general_path(lprop):
+    from msgwam_b200._cabi import lib
+    from msgwam_b200.ensemble import RayEnsemble
+    gmax = int(lib.msgwam_column_max_levels())
+    sc = scenarios.column_ensemble(20011, seed=6, ngrid=gmax + 60, sheared=True, amplitude=0.3)
+    got, want = run_both(lprop, sc, steps=2)
+    ens = RayEnsemble.from_scenario(sc)
+    ens.step(sc.dt, 2)
+    assert_state_close(ens.to_var(), want, ray_tol=1e-12, grid_tol=1e-11, tag="ensemble", start=sc.var())
+
+
 @pytest.mark.parametrize("scale", [1e-262, 1e-255, 1e252])
 def test_chain_rare_operand_route(lprop, scale):
     """Winds of 1e-255 m/s (differences below 1e-250: the invariant-divisor form is not proven there) and 1e252 m/s

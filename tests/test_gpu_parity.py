@@ -282,3 +282,18 @@ def test_fused_cg_rr_is_bit_identical_to_the_library_route(lprop):
             ref = (-mm) * (om * om - f2) / om / (kh2 + mm * mm)
         same = (got == ref) | (np.isnan(got) & np.isnan(ref))
         assert same.all(), (bvf, int((~same).sum()), got[~same][:3], ref[~same][:3])
+
+
+@pytest.mark.parametrize("n,sheared,amplitude", [(1_000_000, False, None), (3_000_000, True, 0.3)])
+def test_full_size_ensembles_vs_oracle(lprop, n, sheared, amplitude):
+    """BASELINE configs[1] at its full size (1e6 ray volumes, constant N, zero wind, G = 1000: the benchmark workload,
+    bit for bit the same ensemble) and a sheared, feeding-back 3e6-ray ensemble: the C oracle steps these in seconds,
+    so parity at full size is checked directly, not through a proxy property."""
+    sc = scenarios.column_ensemble(n, seed=1234, ngrid=1001, sheared=sheared, amplitude=amplitude)
+    sc.install(lprop)
+    orc = oracle.Oracle(sc.oracle_cfg(), nthreads=oracle.max_threads())
+    got, want = lprop.RK3(sc.dt, sc.var()), orc.RK3(sc.dt, sc.var())
+    assert_state_close(got, want, tag=sc.name, start=sc.var())
+    # checksum of the deposit: the mean-flow increment summed over the column equals the oracle's
+    du_g, du_w = np.sum(np.asarray(got[9]) - sc.uu), np.sum(want[9] - sc.uu)
+    assert abs(du_g - du_w) <= 1e-12 * max(abs(du_w), np.max(np.abs(want[9])))

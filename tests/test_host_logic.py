@@ -171,3 +171,22 @@ def test_two_rank_gloo_deposit_allreduce(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
+    our arm's metric / unit / config, an e2e object without copies and the cpu_baseline that describes the run."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--rays", "3000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "ray-steps/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("ray-steps/sec") and d["dtype"] == "f64" and d["value"] > 0
+    for k in ("n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "data", "config", "e2e", "cpu_baseline"):
+        assert k in d, k
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]

@@ -38,6 +38,8 @@ extern "C" {
 #define MSGWAM_E_BADARG      (-1)   /* null pointer / negative size / inconsistent arguments   */
 #define MSGWAM_E_GRID_SIZE   (-2)   /* G too small (< 3) or too large for the fused column kernels */
 #define MSGWAM_E_UNSUPPORTED (-3)   /* mode not handled by this entry point                     */
+#define MSGWAM_E_TIMEOUT     (-4)   /* a bounded device-side wait ran out (grid-wide arrival of the mean-flow slices, or a peer
+                                       in the NVLink all-reduce); the step's results are invalid          */
 
 /* model_config / module globals read on the hot path (SURVEY.md section 5, L:3-11, 380-383, 534, 582-584, 633) */
 typedef struct msgwam_params {

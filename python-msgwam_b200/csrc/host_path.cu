@@ -17,6 +17,7 @@ const char *msgwam_error_string(int code)
     case 0: return "ok";
     case MSGWAM_E_BADARG: return "msgwam: bad argument (null pointer, negative size or inconsistent sizes)";
     case MSGWAM_E_GRID_SIZE: return "msgwam: grid size unsupported (G < 3, or shear tables exceed shared memory)";
+    case MSGWAM_E_TIMEOUT: return "msgwam: a bounded device-side wait timed out (mean-flow slices or a peer of the all-reduce); results invalid";
     case MSGWAM_E_UNSUPPORTED: return "msgwam: mode not supported by this entry point (column kernels need HPROP off and saturate_online off)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "msgwam: unknown error";
     }
@@ -88,7 +89,18 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpyAsync(h_vv_out, d_vvo, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaStreamSynchronize(s);
+    // the error word of the bounded device-side waits travels back with the results
+    double err_word = 0.0;
+    double *d_err = d_work + msgwam_column_error_offset(p->G);
+    e = cudaMemcpyAsync(&err_word, d_err, sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return (int)e;
+    if (err_word != 0.0) {
+        cudaMemsetAsync(d_err, 0, sizeof(double), s);
+        return MSGWAM_E_TIMEOUT;
+    }
+    return 0;
 }
 
 }  // extern "C"

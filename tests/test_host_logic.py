@@ -31,6 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert nm in _cabi.SIGNATURES, "binding missing for " + nm
     assert lib.msgwam_abi_version() == _cabi.ABI_VERSION
     assert b"bad argument" in _cabi.lib.msgwam_error_string(-1)
+    assert b"timed out" in _cabi.lib.msgwam_error_string(-4)
     assert _cabi.lib.msgwam_column_work_doubles(1000) >= 6 * 999
     assert _cabi.lib.msgwam_host_stage_doubles(1000, 100) > 14 * 1000
 

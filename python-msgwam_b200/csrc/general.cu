@@ -65,7 +65,10 @@ __device__ __forceinline__ bool saturation_limit(const msgwam_params_t &p, doubl
 }
 
 // rhs_default's nine ray tendencies (L:629-651), all branches, for ray i: x[9] receives the state, t[9] the tendencies
-__device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9], double t[9])
+// need_sat = false (the fused RK stage with saturate_online off) skips the saturation threshold, whose result the
+// reference multiplies by False (L:647): the tendency is then +0.0 instead of -0.0 where the threshold is exceeded,
+// which no state can tell apart.
+__device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9], double t[9], bool need_sat = true)
 {
     const msgwam_params_t &p = a.p;
     const int G = p.G;
@@ -77,13 +80,13 @@ __device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9]
     const double kh2 = add(mul(kk, kk), mul(ll, ll)), m2 = mul(mm, mm);
     const double vk = add(kh2, m2);
     const double n2 = n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, rr);     // ext: N^2 at the ray centre
-    const double om = omega_from(kh2, m2, f2, n2);
-    const double cgr = dvd(dvd(mul(-mm, sub(mul(om, om), f2)), om), vk);      // L:448 (at the centre)
+    double om;                                                                // L:383
+    const double cgr = cg_rr_fast(kh2, mm, f2, n2, &om);                      // L:448 (at the centre); same roundings
     double cgr_up = cgr, cgr_down = cgr;                                      // cg_rr ignores rr: up == down (L:635-636)
     if (a.bvf != nullptr) {                                                   // ext: N at the two edges
         const double hd = mul(.5, drr);
-        cgr_up = cg_rr_from(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, add(rr, hd)));
-        cgr_down = cg_rr_from(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, sub(rr, hd)));
+        cgr_up = cg_rr_fast(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, add(rr, hd)));
+        cgr_down = cg_rr_fast(kh2, mm, f2, n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, sub(rr, hd)));
     }
     double du_ray, dv_ray;
     shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
@@ -118,10 +121,13 @@ __device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9]
         shear_interp(rr, a.grid, a.bvf, a.bvf, G, p.dz_grid, p.inv_dz_grid, dnr, unused);
         dmm_st = sub(dmm_st, dvd(dvd(mul(mul(nr, dnr), kh2), om), vk));
     }
-    double maxd;
-    const bool hit = saturation_limit(p, p.dt, dens, rr, drr_st, drr, ddrr_st, kk, ll, mm, dmm_st,
-                                      a.r.dkk[i], a.r.dll[i], a.r.rr_mm_area[i], a.grids, a.rhobar, a.bvf, maxd);
-    const double st = hit ? dvd(sub(maxd, dens), p.dt) : 0.0;                 // L:612-615
+    double st = 0.0;
+    if (need_sat) {
+        double maxd;
+        const bool hit = saturation_limit(p, p.dt, dens, rr, drr_st, drr, ddrr_st, kk, ll, mm, dmm_st,
+                                          a.r.dkk[i], a.r.dll[i], a.r.rr_mm_area[i], a.grids, a.rhobar, a.bvf, maxd);
+        st = hit ? dvd(sub(maxd, dens), p.dt) : 0.0;                          // L:612-615
+    }
     x[0] = dens; x[1] = lam; x[2] = phi; x[3] = rr; x[4] = drr; x[5] = kk; x[6] = ll; x[7] = mm; x[8] = dmm;
     t[0] = mul(p.saturate_online ? 1.0 : 0.0, st);                            // L:647
     t[1] = dvd(dvd(cgl, rad), cphi);                                          // L:638
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(NT, 3) stage_rays_kernel(const StageArgs a)
         bool ok = false;
         double x[9], t[9];
         if (live) {
-            ray_rhs(a.r, i, x, t);
+            ray_rhs(a.r, i, x, t, p.saturate_online != 0);
             // wave_projection(var = 0) of the same state, called as L:654-658
             const double hd = mul(.5, x[4]), hm = mul(.5, x[8]);
             rl = sub(x[3], hd); ru = add(x[3], hd);
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(NT, 3) stage_rays_kernel(const StageArgs a)
                 psv = fabs(mul(mul(a.r.r.dkk[i], a.r.r.dll[i]), x[8]));           // L:137
                 const double ff = mul(p.two_rot, sin(x[2]));
                 const double n2 = n2_at(a.r.bvf, a.r.grids, ng, p.inv_dz_grids, p.n2, mul(.5, add(rl, ru)));
-                const double cgr = cg_rr_from(add(mul(x[5], x[5]), mul(x[6], x[6])), mul(.5, add(ml, mu)), mul(ff, ff), n2);
+                const double cgr = cg_rr_fast(add(mul(x[5], x[5]), mul(x[6], x[6])), mul(.5, add(ml, mu)), mul(ff, ff), n2);
                 v0 = mul(mul(cgr, x[5]), x[0]); v1 = mul(mul(cgr, x[6]), x[0]);   // L:148-149
             }
         }

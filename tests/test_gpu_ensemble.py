@@ -192,3 +192,31 @@ def test_post_step_clamp_when_the_packet_saturates(amplitude, steps, tol):
     got = ens.to_var()
     assert max_rel(got[0], var[0]) <= tol
     close(got, var, sc.var(), ray_tol=tol, grid_tol=10 * tol)
+
+
+def test_full_driver_run_1440_steps_on_the_device():
+    """The driver's whole run (nt_max = 1440, R:157-188) on the device, against the unmodified driver's history.
+    Tolerances follow the reference's own noise floor (the reference against itself with the
+    rays permuted differs by 5.9e-14 in m at step 720 and 4.3e-8 at step 1440)."""
+    from conftest import load_golden
+    from helpers import field_rel, max_rel
+    from msgwam_b200.ensemble import History, RayEnsemble
+    d = load_golden("driver_history.npz")
+    sc = scenarios.default_column()
+    ens = RayEnsemble.from_scenario(sc)
+    hist = History(ens, nsnap=5, every=360)
+    ens.advance(sc.dt, 1440, saturate=True, history=hist)
+    h = hist.to_host()
+    steps = list(d["steps"])
+    for nt, tol in ((360, 1e-10), (720, 1e-10), (1440, 5e-6)):
+        k, j = steps.index(nt), list(h["steps"]).index(nt)
+        for nm in ("dens", "rr", "mm", "drr", "dmm"):
+            assert max_rel(h[nm][j], d[nm][k]) <= tol, (nt, nm, max_rel(h[nm][j], d[nm][k]))
+        assert field_rel(h["uu"][j], d["uu"][k]) <= tol, nt
+    # the conservation diagnostic of the driver (R:198-240) on the final state: projected wave action
+    import msgwam_b200.libprop as lprop
+    sc.install(lprop)
+    v = ens.to_var()
+    wa = lprop.wave_projection(v[0], v[1], v[2], v[3] - .5 * v[4], v[3] + .5 * v[4], v[5], v[6], v[7] - .5 * v[8],
+                               v[7] + .5 * v[8], sc.dkk, sc.dll, v[8], sc.grid, var=2)
+    assert np.all(np.isfinite(wa)) and wa.max() > 0

@@ -115,3 +115,18 @@ def test_projection_corner_cases():
     assert np.isclose(w(1)[0], 0.15)                                         # [100,350]: spurious |350-500|/1000
     assert np.count_nonzero(w(2)) == 0                                       # [98600,99400]: top cell never written
     assert np.allclose(w(3)[[96, 97]], 1.0) and np.count_nonzero(w(3)) == 2  # clamped straddler
+
+
+def test_driver_fixture_matches_the_known_answers_recorded_in_the_survey():
+    """SURVEY.md section 4 lists values read off the unmodified raytracer.py run (numpy 2.3.5); the committed fixture
+    must reproduce them, so the fixture itself is pinned to an independent record."""
+    d = load_golden("driver_history.npz")
+    steps = list(d["steps"])
+    k1, kend = steps.index(1), steps.index(1440)
+    assert np.array_equal(d["rr"][k1][:3], [219.07715034112215, 469.07715034112215, 719.0771503411221])
+    assert np.allclose(d["mm"][k1][:3], -0.00125665223824475, rtol=1e-14, atol=0)       # the survey printed 15 digits
+    assert np.array_equal(d["uu"][k1][38:42], [-1.3771329439311946, -0.587158015003212, 0.6489099624965707, 1.858935033568595])
+    assert np.allclose(d["rr"][kend][:3], [92862.22980969641, 92862.41977331725, 92905.23567557707], rtol=1e-13, atol=0)
+    assert np.allclose(d["mm"][kend][:3], [-0.00304211131909678, -0.00302430454016963, -0.00299897575710608], rtol=1e-14, atol=0)
+    assert np.allclose(d["dens"][kend][:3], [8.0293785331725159e9, 1.2631985534866663e10, 1.9293364183825668e10], rtol=1e-13, atol=0)
+    assert abs(float(d["wa_max"]) - 3.8994466052014998) <= 1e-12 and abs(float(d["flux_diag_absmax"]) - 1.8943901432301569) <= 1e-12

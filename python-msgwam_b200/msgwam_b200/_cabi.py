@@ -68,6 +68,8 @@ SIGNATURES = {
     "msgwam_column_pass_b_p2p": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Peers), _vp]),
     "msgwam_column_finish_p2p": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Peers), _vp]),
     "msgwam_column_step_p2p": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Peers), _vp]),
+    "msgwam_column_step_nz": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 9 + [_vp]),
+    "msgwam_column_nz_max_levels": (_i32, []),
     "msgwam_column_error_offset": (_i64, [_i32]),
     "msgwam_column_step": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_debug_cg_rr_fast": (ctypes.c_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _i64, _vp]),

@@ -44,6 +44,7 @@ class Engine:
         self._derived = None
         self._scratch = None
         self._gmax = None
+        self._gmax_nz = None
         self.launches = 0          # kernels launched through this engine (bench.py reports it)
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -97,12 +98,38 @@ class Engine:
             self._gmax = int(lib.msgwam_column_max_levels())
         return self._gmax
 
-    def ray_scratch(self, n: int):
-        """3 n doubles for the stage-1 hand-over between the two sweeps (msgwam_rays_t.stage1)."""
+    def ray_scratch(self, n: int, per_ray: int = 3):
+        """per_ray * n doubles for the stage-1 hand-over between the two sweeps (msgwam_rays_t.stage1): 3 per ray,
+        7 with an N(z) profile."""
         t = self._scratch
-        if t is None or t.numel() < 3 * n:
-            t = self._scratch = self.empty(max(3 * n, 1))
+        if t is None or t.numel() < per_ray * n:
+            t = self._scratch = self.empty(max(per_ray * n, 1))
         return t
+
+    def column_nz_max_levels(self) -> int:
+        if self._gmax_nz is None:
+            self._gmax_nz = int(lib.msgwam_column_nz_max_levels())
+        return self._gmax_nz
+
+    def column_step_nz(self, p: Params, state, dkk, dll, uu, vv, grid_devs):
+        """The fused column step with an N(z) profile (grid_devs carries it as its fifth entry); one GPU.
+        Returns (rr, drr, mm, dmm, uu, vv) after the step."""
+        dens, lam, phi, rr, drr, kk, ll, mm, dmm = state
+        n = rr.numel()
+        ff, pkl = self.derived_statics(phi, dkk, dll, p.two_rot)
+        rays = Rays()
+        for k, t in (("dens", dens), ("phi", phi), ("rr", rr), ("drr", drr), ("kk", kk), ("ll", ll), ("mm", mm),
+                     ("dmm", dmm), ("dkk", dkk), ("dll", dll), ("ff", ff), ("pkl", pkl)):
+            setattr(rays, k, t.data_ptr())
+        rays.stage1 = self.ray_scratch(n, 7).data_ptr()
+        g = self.grid_struct(grid_devs)
+        work = self.column_work(p.G)
+        outs = [self.empty(n) for _ in range(4)]
+        uu_out, vv_out = self.empty(p.G), self.empty(p.G)
+        check(lib.msgwam_column_step_nz(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), *[self.ptr(t) for t in outs],
+                                        self.ptr(uu_out), self.ptr(vv_out), self.stream), "msgwam_column_step_nz")
+        self.launches += 2
+        return outs[0], outs[1], outs[2], outs[3], uu_out, vv_out
 
     def host_stage(self, n: int, G: int):
         key = (n, G)

@@ -95,20 +95,21 @@ class RayEnsemble:
             c = self._params_cache = (dt, _cabi.snapshot_params(dt, grid=self.grid_host, grids=self.grids_host, **self.cfg))
         return c[1]
 
-    def _rays(self) -> _cabi.Rays:
+    def _rays(self, hand: int = 3) -> _cabi.Rays:
+        """The ray store as a msgwam_rays_t; `hand` doubles per ray of hand-over scratch (3; 7 with an N(z) profile)."""
         key = (self._slab.data_ptr(), self.n, None if self._stage1 is None else self._stage1.data_ptr())
-        if self._rays_cache is not None and self._rays_cache[0] == key and self._stage1 is not None and self._stage1.numel() >= 3 * self.n:
+        if self._rays_cache is not None and self._rays_cache[0] == key and self._stage1 is not None and self._stage1.numel() >= hand * self.n:
             return self._rays_cache[1]
-        r = self._build_rays()
+        r = self._build_rays(hand)
         self._rays_cache = ((self._slab.data_ptr(), self.n, self._stage1.data_ptr()), r)
         return r
 
-    def _build_rays(self) -> _cabi.Rays:
+    def _build_rays(self, hand: int = 3) -> _cabi.Rays:
         r = _cabi.Rays()
         for nm in STATE + STATICS + ("ff", "pkl"):
             setattr(r, nm, self.field(nm).data_ptr())
-        if self._stage1 is None or self._stage1.numel() < 3 * self.n:
-            self._stage1 = self.eng.empty(max(3 * self.cap, 1))     # stage-1 hand-over between the two sweeps
+        if self._stage1 is None or self._stage1.numel() < hand * self.n:
+            self._stage1 = self.eng.empty(max(hand * self.cap, 1))  # stage-1 hand-over between the two sweeps
         r.stage1 = self._stage1.data_ptr()
         return r
 
@@ -123,6 +124,20 @@ class RayEnsemble:
         p = self.params(dt)
         g = eng.grid_struct(self.grid_devs)
         column = not p.hprop and not p.saturate_online and len(self.grid_devs) == 4 and self.G <= eng.column_max_levels()
+        sharded = self.dist is not None and self.dist.get_world_size() > 1
+        column_nz = (not p.hprop and not p.saturate_online and len(self.grid_devs) == 5 and not sharded and
+                     self.G <= eng.column_nz_max_levels())
+        if column_nz:                               # N(z) extension, fused; in place
+            rays = self._rays(hand=7)
+            P = eng.ptr
+            for _ in range(nsteps):
+                check(lib.msgwam_column_step_nz(p, rays, self.n, g, P(self.uu), P(self.vv), P(self.work), P(self.field("rr")),
+                                                P(self.field("drr")), P(self.field("mm")), P(self.field("dmm")), P(self._uu2),
+                                                P(self._vv2), eng.stream), "msgwam_column_step_nz")
+                eng.launches += 2
+                self.uu, self._uu2 = self._uu2, self.uu
+                self.vv, self._vv2 = self._vv2, self.vv
+            return
         nc = self.G - 1
         if column:
             rays = self._rays()

@@ -475,14 +475,23 @@ def RK3(dt, var):
     eng = _engine()
     p = _params(dt)
     like_dev = _any_dev(eng, *var)
-    column = not p.hprop and not p.saturate_online and _bvf_profile() is None and p.G <= eng.column_max_levels()
+    prof = _bvf_profile()
+    column = not p.hprop and not p.saturate_online and prof is None and p.G <= eng.column_max_levels()
+    column_nz = not p.hprop and not p.saturate_online and prof is not None and p.G <= eng.column_nz_max_levels()
     if column and not like_dev:
         return _rk3_numpy_column(eng, p, var)
     n = _size(var[3])
     state = [eng.dev(x, n) for x in var[:9]]
     uu, vv = eng.dev(var[9], p.G), eng.dev(var[10], p.G)
     gd = _grid_devs(eng)
-    if column:
+    if column_nz:
+        # N(z) extension: fused column step with the profile (rr, drr, mm, dmm evolve)
+        dkk, dll = eng.dev(statics['dkk'], n), eng.dev(statics['dll'], n)
+        statics['rr_mm_area']
+        rr_new, drr_new, mm_new, dmm_new, uu_new, vv_new = eng.column_step_nz(p, state, dkk, dll, uu, vv, gd)
+        slots = [state[0].clone(), state[1].clone(), state[2].clone(), rr_new, drr_new, state[5].clone(),
+                 state[6].clone(), mm_new, dmm_new, uu_new, vv_new]
+    elif column:
         dkk, dll = eng.dev(statics['dkk'], n), eng.dev(statics['dll'], n)
         statics['rr_mm_area']
         rr_new, mm_new, uu_new, vv_new = eng.column_step(p, state, dkk, dll, uu, vv, gd)

@@ -117,3 +117,25 @@ def test_gpu_varying_profile_vs_oracle(lprop, case):
     st = lprop.saturation(sc.dt, dens, rr, drr * 0 + .1, drr, drr * 0, kk, ll, mm, mm * 1e-6, direct=True)
     sw = orc.saturation(sc.dt, dens, rr, drr * 0 + .1, drr, drr * 0, kk, ll, mm, mm * 1e-6, direct=True)
     assert max_rel(st, sw) <= 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,ngrid,shuffled", [(60011, 501, False), (60011, 1001, True), (257, 34, False)])
+def test_gpu_fused_column_step_with_profile_vs_oracle(lprop, n, ngrid, shuffled):
+    """The fused two-sweep column step with an N(z) profile (msgwam_column_step_nz: rr, drr, mm, dmm evolve) on a
+    sheared, feeding-back ensemble, three steps, through lprop.RK3 and in place through RayEnsemble."""
+    from msgwam_b200 import scenarios
+    from msgwam_b200.ensemble import RayEnsemble
+    from test_gpu_parity import assert_state_close
+    sc = scenarios.column_ensemble(n, seed=77, ngrid=ngrid, sheared=True, shuffled=shuffled, amplitude=0.3)
+    sc.model = dict(sc.model, bvf=n_profile(sc.grids))
+    sc.install(lprop)
+    orc = oracle.Oracle(sc.oracle_cfg())
+    got = want = sc.var()
+    for step in range(3):
+        got, want = lprop.RK3(sc.dt, got), orc.RK3(sc.dt, want)
+        assert_state_close(got, want, ray_tol=1e-12, grid_tol=1e-11, tag="step %d" % (step + 1), start=sc.var())
+    assert np.max(np.abs(np.asarray(got[4]) - sc.state[4])) > 0 and np.max(np.abs(np.asarray(got[8]) - sc.state[8])) > 0
+    ens = RayEnsemble.from_scenario(sc)
+    ens.step(sc.dt, 3)
+    assert_state_close(ens.to_var(), want, ray_tol=1e-12, grid_tol=1e-11, tag="ensemble", start=sc.var())

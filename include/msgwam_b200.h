@@ -156,11 +156,14 @@ int msgwam_column_step_p2p(const msgwam_params_t *p, const msgwam_rays_t *rays, 
                            double *d_uu_out, double *d_vv_out, const msgwam_peers_t *peers, void *stream);
 /* N(z) EXTENSION (no counterpart in the reference): the same two launches with a buoyancy-frequency profile grid->bvf
  * (N on grids).  N^2 differs between the centre and the edges of a ray volume, so rr, drr, mm and dmm all evolve;
- * rays->stage1 must hold 7 * n doubles.  One GPU; G <= msgwam_column_nz_max_levels(). */
+ * rays->stage1 must hold 7 * n doubles.  G <= msgwam_column_nz_max_levels().  With `peers` (several GPUs) the
+ * all-reduces of the deposit run inside the sweeps, epochs peers->epoch and peers->epoch + 1, as in
+ * msgwam_column_step_p2p. */
 int msgwam_column_step_nz(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
                           const msgwam_grid_t *grid, const double *d_uu, const double *d_vv, double *d_work,
                           double *d_rr_out, double *d_drr_out, double *d_mm_out, double *d_dmm_out,
-                          double *d_uu_out, double *d_vv_out, void *stream);
+                          double *d_uu_out, double *d_vv_out, const msgwam_peers_t *peers /* NULL: one GPU */,
+                          void *stream);
 int32_t msgwam_column_nz_max_levels(void);
 /* offset (in doubles) inside d_work of the error word set by a timed-out peer exchange (0.0 = ok) */
 int64_t msgwam_column_error_offset(int32_t G);

@@ -68,7 +68,7 @@ SIGNATURES = {
     "msgwam_column_pass_b_p2p": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Peers), _vp]),
     "msgwam_column_finish_p2p": (ctypes.c_int, [_PP, _GP, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Peers), _vp]),
     "msgwam_column_step_p2p": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Peers), _vp]),
-    "msgwam_column_step_nz": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 9 + [_vp]),
+    "msgwam_column_step_nz": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 9 + [ctypes.POINTER(Peers), _vp]),
     "msgwam_column_nz_max_levels": (_i32, []),
     "msgwam_column_error_offset": (_i64, [_i32]),
     "msgwam_column_step": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -127,7 +127,7 @@ class Engine:
         outs = [self.empty(n) for _ in range(4)]
         uu_out, vv_out = self.empty(p.G), self.empty(p.G)
         check(lib.msgwam_column_step_nz(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), *[self.ptr(t) for t in outs],
-                                        self.ptr(uu_out), self.ptr(vv_out), self.stream), "msgwam_column_step_nz")
+                                        self.ptr(uu_out), self.ptr(vv_out), None, self.stream), "msgwam_column_step_nz")
         self.launches += 2
         return outs[0], outs[1], outs[2], outs[3], uu_out, vv_out
 

@@ -125,15 +125,16 @@ class RayEnsemble:
         g = eng.grid_struct(self.grid_devs)
         column = not p.hprop and not p.saturate_online and len(self.grid_devs) == 4 and self.G <= eng.column_max_levels()
         sharded = self.dist is not None and self.dist.get_world_size() > 1
-        column_nz = (not p.hprop and not p.saturate_online and len(self.grid_devs) == 5 and not sharded and
-                     self.G <= eng.column_nz_max_levels())
+        column_nz = (not p.hprop and not p.saturate_online and len(self.grid_devs) == 5 and
+                     (not sharded or self.exchange is not None) and self.G <= eng.column_nz_max_levels())
         if column_nz:                               # N(z) extension, fused; in place
             rays = self._rays(hand=7)
             P = eng.ptr
             for _ in range(nsteps):
                 check(lib.msgwam_column_step_nz(p, rays, self.n, g, P(self.uu), P(self.vv), P(self.work), P(self.field("rr")),
                                                 P(self.field("drr")), P(self.field("mm")), P(self.field("dmm")), P(self._uu2),
-                                                P(self._vv2), eng.stream), "msgwam_column_step_nz")
+                                                P(self._vv2), self.exchange.next(2) if self.exchange is not None else None,
+                                                eng.stream), "msgwam_column_step_nz")
                 eng.launches += 2
                 self.uu, self._uu2 = self._uu2, self.uu
                 self.vv, self._vv2 = self._vv2, self.vv

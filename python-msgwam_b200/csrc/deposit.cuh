@@ -95,11 +95,37 @@ __device__ __forceinline__ double cell_weight(int c, double rl, double ru, doubl
 // shared memory, or the output itself), one fp64 atomicAdd each; `used`, if given, marks the histogram dirty for the
 // merge at the end of the CTA.  (Measured and rejected: both components side by side with ONE 128-bit
 // compare-and-swap per cell, ATOMS.CAS.128 -- 2-3x slower than two 64-bit CAS loops; fp64 RED straight to the global
-// deposit -- 2.5x slower once the rays are dispersed, 6x for unordered rays.)
+// deposit -- 2.5x slower once the rays are dispersed, 6x for unordered rays; a 96-bit fixed-point histogram fed with
+// native 32-bit ATOMS.ADD and carries -- exact and 2.5x the lane-add rate of the CAS loop in isolation
+// (tools/micro/smem_atomics.cu), but its conversions and carry chains cost more issue slots than the CAS unit costs
+// time: 198 instead of 145 us per step for a dispersed ensemble.)
 struct SplitTargets {
     double *s0, *s1; int *used;
     __device__ __forceinline__ void mark() const { if (used != nullptr) *used = 1; }
     __device__ __forceinline__ void add(int c, double x, double y) const { atomicAdd(s0 + c, x); atomicAdd(s1 + c, y); }
+    // Two cells at once, optimistically: the four read-add-CAS sequences are issued side by side so that their
+    // shared-memory round trips overlap (atomicAdd's own CAS loop serialises them); a CAS that lost against another
+    // lane falls back to atomicAdd.  c1 is ignored unless `two`.
+    __device__ __forceinline__ void add2(int c0, double x0, double y0, bool two, int c1, double x1, double y1) const
+    {
+        typedef unsigned long long u64;
+        u64 *p0 = reinterpret_cast<u64 *>(s0 + c0), *p1 = reinterpret_cast<u64 *>(s1 + c0);
+        u64 *p2 = reinterpret_cast<u64 *>(s0 + c1), *p3 = reinterpret_cast<u64 *>(s1 + c1);
+        const u64 o0 = *reinterpret_cast<volatile u64 *>(p0), o1 = *reinterpret_cast<volatile u64 *>(p1);
+        u64 o2 = 0, o3 = 0;
+        if (two) { o2 = *reinterpret_cast<volatile u64 *>(p2); o3 = *reinterpret_cast<volatile u64 *>(p3); }
+        const u64 n0 = __double_as_longlong(mw::add(__longlong_as_double(o0), x0));
+        const u64 n1 = __double_as_longlong(mw::add(__longlong_as_double(o1), y0));
+        const u64 n2 = __double_as_longlong(mw::add(__longlong_as_double(o2), x1));
+        const u64 n3 = __double_as_longlong(mw::add(__longlong_as_double(o3), y1));
+        const u64 g0 = atomicCAS(p0, o0, n0), g1 = atomicCAS(p1, o1, n1);
+        u64 g2 = o2, g3 = o3;
+        if (two) { g2 = atomicCAS(p2, o2, n2); g3 = atomicCAS(p3, o3, n3); }
+        if (g0 != o0) atomicAdd(s0 + c0, x0);
+        if (g1 != o1) atomicAdd(s1 + c0, y0);
+        if (g2 != o2) atomicAdd(s0 + c1, x1);
+        if (g3 != o3) atomicAdd(s1 + c1, y1);
+    }
 };
 
 template <int WIN, class Sink>
@@ -164,9 +190,11 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
     } else if (ok) {
         // outlier lane / unordered rays: add to the CTA histogram directly
         sink.mark();
-        for (int c = nlow; c < nup; ++c) {
-            const double tc = cell_weight(c, rl, ru, psv, dz, rdz, g);
-            sink.add(c, mul(tc, v0), mul(tc, v1));
+        for (int c = nlow; c < nup; c += 2) {
+            const bool two = c + 1 < nup;
+            const int c1 = two ? c + 1 : c;
+            const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g), t1 = cell_weight(c1, rl, ru, psv, dz, rdz, g);
+            sink.add2(c, mul(t0, v0), mul(t0, v1), two, c1, mul(t1, v0), mul(t1, v1));
         }
     }
 }

@@ -131,8 +131,10 @@ int msgwam_column_finish(const msgwam_params_t *p, const msgwam_grid_t *grid,
  * themselves with one-shot pushes over NVLink peer memory.  inbox[r] is rank r's inbox buffer
  * (msgwam_p2p_inbox_doubles(G, world) doubles, zero-initialised once, allocated in symmetric / IPC memory)
  * as mapped into THIS process; epoch must be identical on all ranks and increase by one per reduction
- * (pass_b_p2p and finish_p2p each perform one).  A peer that does not answer within ~20 s sets the error
- * word returned by msgwam_column_error() instead of hanging the GPU. */
+ * (pass_b_p2p and finish_p2p each perform one).  Every value travels as a 16-byte cell {low word, flag, high word,
+ * flag} with flag = epoch | 2^31, so a receiver polls the data itself (2 parities x world slots x 4 (G - 1) cells per
+ * inbox).  A peer that does not answer within ~20 s sets the error word returned by msgwam_column_error()
+ * instead of hanging the GPU. */
 #define MSGWAM_MAX_PEERS 16
 typedef struct msgwam_peers {
     int32_t world, rank;
@@ -147,9 +149,11 @@ int msgwam_column_pass_b_p2p(const msgwam_params_t *p, const msgwam_rays_t *rays
 int msgwam_column_finish_p2p(const msgwam_params_t *p, const msgwam_grid_t *grid,
                              const double *d_uu, const double *d_vv, double *d_work,
                              double *d_uu_out, double *d_vv_out, const msgwam_peers_t *peers, void *stream);
-/* Multi-GPU, fully fused: the same two launches as msgwam_column_step; the last CTA of each sweep all-reduces this
- * GPU's deposit over the peer inboxes (epochs peers->epoch and peers->epoch + 1: advance the epoch by TWO per
- * call) before the mean-flow chain (inside pass B) / the finish (tail of pass B) run on the sums. */
+/* Multi-GPU, fully fused: the same two launches as msgwam_column_step (epochs peers->epoch and peers->epoch + 1:
+ * advance the epoch by TWO per call).  The last CTA of pass A pushes this GPU's D0 | D1 to every inbox and retires;
+ * each CTA of pass B polls its own inbox for the cells its slice of the mean-flow chain reads and sums them in rank
+ * order.  The last CTA of pass B pushes D2, collects the sums and runs the finish.  d_work's D0 | D1 hold this
+ * GPU's partial sums only. */
 int msgwam_column_step_p2p(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
                            const msgwam_grid_t *grid, const double *d_uu, const double *d_vv,
                            double *d_work, double *d_rr_out, double *d_mm_out,

@@ -39,9 +39,9 @@ A_PASS_A = 72.0    # pass A: 9 fields read (dens, ff, rr, drr, kk, ll, mm, dmm, 
                    # (stage-1 increments, cg_rr(r1)) is implementation traffic, not algorithmic
 A_PASS_B = 88.0    # pass B: the same 9 fields read + rr, mm written (+ the 24 B/ray hand-over read back)
 # dram__bytes_read.sum + dram__bytes_write.sum per ray from the committed `ncu --set full` capture at 1e6 rays
-# (profiles/r01b_column_pass_ncu_full_summary.json): pass A 72.1 + 5.5 MB, pass B 96.2 + 5.5 MB
-NCU_TRAFFIC_PER_RAY = {"A": 77.6, "B": 101.7}
-NCU_TRAFFIC_SOURCE = "ncu --set full at 1e6 rays, profiles/r01b_column_pass_ncu_full_summary.json"
+# (profiles/r01d_column_pass_ncu_full_summary.json): pass A 72.1 + 5.5 MB, pass B 96.2 + 5.5 MB
+NCU_TRAFFIC_PER_RAY = {"A": 79.9, "B": 102.8}
+NCU_TRAFFIC_SOURCE = "ncu --set full at 1e6 rays, profiles/r01d_column_pass_ncu_full_summary.json"
 
 
 def measured_peaks():
@@ -276,6 +276,8 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- per-kernel timing for the roofline (single rank's kernels; no collectives inside) --------
     ka, kb, kf = [], [], []
+    flush.zero_(); pass_a(); reduce_(ens.work[:4 * nc]); pass_b(); reduce_(ens.work[4 * nc:6 * nc]); finish()   # first launch of the split-form kernels
+    torch.cuda.synchronize()
     for _ in range(max(3, min(args.steps, 20))):
         flush.zero_()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -284,7 +286,7 @@ def run_ours(args, rank, local_rank, world):
         fin0.record(); finish(); e[3].record()
         torch.cuda.synchronize()
         ka.append(e[0].elapsed_time(e[1])); kb.append(pass_b_start.elapsed_time(e[2])); kf.append(fin0.elapsed_time(e[3]))
-    t_a, t_b, t_f = (statistics.mean(x) * 1e-3 for x in (ka, kb, kf))
+    t_a, t_b, t_f = (statistics.mean(x) * 1e-3 for x in (ka, kb, kf))     # average launch duration, as the contract asks
 
     # ---- e2e: the reference-facing call with host buffers ------------------------------------------
     def pinned(a):
@@ -400,8 +402,8 @@ def run_ours(args, rank, local_rank, world):
                      "traffic": NCU_TRAFFIC_PER_RAY[dom] * n, "traffic_source": NCU_TRAFFIC_SOURCE,
                      "kernel": kernels[dom]["name"], "algorithmic_bytes_per_ray": kernels[dom]["alg"],
                      "kernel_ms": kernels[dom]["ms"], "peak_source": peak_src,
-                     "note": "the sweeps are bound by instruction issue / fp64 latency, not by HBM (ncu: issue slots 60 % busy, "
-                             "fp64 pipe 37 %, DRAM 22 %): see profiles/r01_summary.md",
+                     "note": "the sweeps are bound by instruction issue / fp64 latency, not by HBM (ncu: issue slots 59 % busy, "
+                             "fp64 pipe 37 %, DRAM 23 %): see profiles/r01_summary.md",
                      "other_kernels": {kernels[oth]["name"]: {"ms": kernels[oth]["ms"],
                                                               "achieved_gbs": kernels[oth]["alg"] * n / (kernels[oth]["ms"] * 1e-3) / 1e9,
                                                               "algorithmic_bytes_per_ray": kernels[oth]["alg"],

@@ -6,6 +6,7 @@
 // values in column mode (their tendencies are exactly zero, L:638-645 with HPROP off), so the shim
 // returns copies of the inputs for those slots and they are never moved over PCIe.
 #include "common.cuh"
+#include <string.h>
 
 extern "C" {
 
@@ -24,6 +25,25 @@ const char *msgwam_error_string(int code)
 }
 
 static inline int64_t pad32(int64_t n) { return (n + 31) & ~(int64_t)31; }
+
+// Page-locked staging for the grid-sized arguments of msgwam_rk3_column_host (one block per process, grown on demand;
+// every call ends with a stream synchronisation, so no copy is in flight when it is reallocated).
+static double *g_pin = nullptr;
+static size_t g_pin_cap = 0;
+static double *pinned_block(size_t doubles)
+{
+    if (doubles > g_pin_cap) {
+        if (g_pin) cudaFreeHost(g_pin);
+        g_pin = nullptr; g_pin_cap = 0;
+        const size_t cap = doubles < 65536 ? 65536 : doubles;
+        if (cudaHostAlloc(reinterpret_cast<void **>(&g_pin), cap * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+            g_pin = nullptr;
+            return nullptr;
+        }
+        g_pin_cap = cap;
+    }
+    return g_pin;
+}
 
 int64_t msgwam_host_stage_doubles(int64_t n, int32_t G)
 {
@@ -64,8 +84,23 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
             if (e != cudaSuccess) return (int)e;                                                       \
         }                                                                                              \
     } while (0)
-    MW_H2D(d_grid, h_grid, G + 1); MW_H2D(d_grids, h_grids, G); MW_H2D(d_rho, h_rhobar, G); MW_H2D(d_pg, h_pg, 2 * G);
-    MW_H2D(d_uu, h_uu, G); MW_H2D(d_vv, h_vv, G);
+    // The grid-sized inputs are ordinary (pageable) numpy arrays: six cudaMemcpyAsync calls from pageable memory are
+    // six staged, blocking copies (~100 us in all).  They are gathered into one page-locked block laid out like the
+    // device region and go up with ONE asynchronous copy; uu, vv and the error word come back the same way.
+    const int64_t gblock = pad32(G + 1) + 6 * gp;                 // grid | grids | rhobar | pg (2) | uu | vv
+    double *pin = pinned_block((size_t)(gblock + 2 * gp + 8));
+    if (!pin) return (int)cudaErrorMemoryAllocation;
+    {
+        double *q = pin;
+        memcpy(q, h_grid, (size_t)(G + 1) * sizeof(double)); q += pad32(G + 1);
+        memcpy(q, h_grids, (size_t)G * sizeof(double)); q += gp;
+        memcpy(q, h_rhobar, (size_t)G * sizeof(double)); q += gp;
+        memcpy(q, h_pg, (size_t)(2 * G) * sizeof(double)); q += 2 * gp;                  // (2, G) contiguous, as the kernels index it
+        memcpy(q, h_uu, (size_t)G * sizeof(double)); q += gp;
+        memcpy(q, h_vv, (size_t)G * sizeof(double));
+    }
+    e = cudaMemcpyAsync(d_grid, pin, (size_t)gblock * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int)e;
     MW_H2D(d_phi, h_state[2], n);
     if (h_dkk) { MW_H2D(d_dkk, h_dkk, n); MW_H2D(d_dll, h_dll, n); }   // NULL: reuse the statics left in d_stage
     int rc = msgwam_derive_statics(d_phi, d_dkk, d_dll, d_ff, d_pkl, n, p->two_rot, stream);
@@ -85,17 +120,18 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
         e = cudaMemcpyAsync(h_mm_out, d_mmo, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) return (int)e;
     }
-    e = cudaMemcpyAsync(h_uu_out, d_uuo, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, s);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpyAsync(h_vv_out, d_vvo, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, s);
+    double *pin_out = pin + gblock;                               // uu_out | vv_out | error word
+    e = cudaMemcpyAsync(pin_out, d_uuo, (size_t)(2 * gp) * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) return (int)e;
     // the error word of the bounded device-side waits travels back with the results
-    double err_word = 0.0;
     double *d_err = d_work + msgwam_column_error_offset(p->G);
-    e = cudaMemcpyAsync(&err_word, d_err, sizeof(double), cudaMemcpyDeviceToHost, s);
+    e = cudaMemcpyAsync(pin_out + 2 * gp, d_err, sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) return (int)e;
     e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return (int)e;
+    memcpy(h_uu_out, pin_out, (size_t)G * sizeof(double));
+    memcpy(h_vv_out, pin_out + gp, (size_t)G * sizeof(double));
+    const double err_word = pin_out[2 * gp];
     if (err_word != 0.0) {
         cudaMemsetAsync(d_err, 0, sizeof(double), s);
         return MSGWAM_E_TIMEOUT;

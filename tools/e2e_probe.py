@@ -21,11 +21,23 @@ print("pageable   64 MiB  H2D %.1f GB/s   D2H %.1f GB/s" % (bw(64 << 20, "h2d", 
 
 import msgwam_b200.libprop as lprop
 from msgwam_b200 import scenarios
+def pinned(a):
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True); t.numpy()[...] = a; return t
+for n in (1000, 100000):          # the fixed cost of a host call
+    sc = scenarios.column_ensemble(n, seed=1234, ngrid=1001)
+    sc.install(lprop)
+    keep = [pinned(np.ascontiguousarray(a)) for a in list(sc.state) + [sc.uu, sc.vv, sc.dkk, sc.dll, sc.rr_mm_area]]
+    var = np.empty(11, dtype=object)
+    for i in range(11): var[i] = keep[i].numpy()
+    lprop.set_statics(dkk=keep[11].numpy(), dll=keep[12].numpy(), rr_mm_area=keep[13].numpy())
+    for _ in range(3): lprop.RK3(sc.dt, var)
+    ts = []
+    for _ in range(20):
+        t0 = time.perf_counter(); out = lprop.RK3(sc.dt, var); ts.append(time.perf_counter() - t0)
+    print("RK3 host call at n = %d: median %.3f ms  min %.3f ms" % (n, np.median(ts) * 1e3, min(ts) * 1e3))
 n = 1000000
 sc = scenarios.column_ensemble(n, seed=1234, ngrid=1001)
 sc.install(lprop)
-def pinned(a):
-    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True); t.numpy()[...] = a; return t
 keep = [pinned(np.ascontiguousarray(a)) for a in list(sc.state) + [sc.uu, sc.vv, sc.dkk, sc.dll, sc.rr_mm_area]]
 var = np.empty(11, dtype=object)
 for i in range(11): var[i] = keep[i].numpy()

@@ -253,6 +253,17 @@ int msgwam_saturation_step(const msgwam_params_t *p, int64_t n, const double *d_
                            const double *d_dkk, const double *d_dll, const double *d_area,
                            const double *d_grids, const double *d_rhobar, const double *d_bvf /* NULL or N on grids */,
                            double *d_dens_out, void *stream);
+/* The same clamp for a driver that stepped OUT of place (rr_new, mm_new in scratch): the kernel also copies rr_new to
+ * d_rr_commit and mm_new to d_mm_commit (each may be NULL, and may alias d_rr_old / d_mm_old -- the ray store), which
+ * replaces the three copies of the old state a driver loop would otherwise make before every in-place step. */
+int msgwam_saturation_step_commit(const msgwam_params_t *p, int64_t n, const double *d_dens,
+                                  const double *d_rr_old, const double *d_rr_new,
+                                  const double *d_drr_old, const double *d_drr_new,
+                                  const double *d_kk, const double *d_ll,
+                                  const double *d_mm_old, const double *d_mm_new,
+                                  const double *d_dkk, const double *d_dll, const double *d_area,
+                                  const double *d_grids, const double *d_rhobar, const double *d_bvf /* NULL or N on grids */,
+                                  double *d_dens_out, double *d_rr_commit, double *d_mm_commit, void *stream);
 
 /* ---- point functions (replace omega L:369, cg_rr L:434, cg_lambda L:386, cg_phi L:410,
  *      dk_dt L:451, dl_dt L:474, dm_dt L:502, gradients L:328) ------------------------------

@@ -82,6 +82,7 @@ SIGNATURES = {
     "msgwam_wave_projection": (ctypes.c_int, [_i32, _PP, _i64] + [_vp] * 12 + [_i32, _dbl, _dbl, _vp, _vp, _vp, _vp]),
     "msgwam_saturation": (ctypes.c_int, [_PP, _i64, _i32] + [_vp] * 16 + [_vp]),
     "msgwam_saturation_step": (ctypes.c_int, [_PP, _i64] + [_vp] * 16 + [_vp]),
+    "msgwam_saturation_step_commit": (ctypes.c_int, [_PP, _i64] + [_vp] * 18 + [_vp]),
     "msgwam_pointwise": (ctypes.c_int, [_i32, _PP, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _GP, _vp, _vp, _vp, _vp]),
     "msgwam_compact_scratch_bytes": (_i64, [_i64]),
     "msgwam_flag_rays": (ctypes.c_int, [_PP, _i64, _vp, _vp, _vp, _dbl, _vp, _vp]),

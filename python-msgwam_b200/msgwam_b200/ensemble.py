@@ -118,12 +118,18 @@ class RayEnsemble:
             self.dist.all_reduce(t)
 
     # ---- stepping ---------------------------------------------------------------------------------
-    def step(self, dt, nsteps=1):
-        """Advance rays and mean flow in place by nsteps RK3 steps (reference RK3 + rhs_default semantics)."""
+    def _is_column(self, p):
+        """The fused constant-N column step applies (HPROP off, online saturation off, scalar N, grid fits)."""
+        return not p.hprop and not p.saturate_online and len(self.grid_devs) == 4 and self.G <= self.eng.column_max_levels()
+
+    def step(self, dt, nsteps=1, _outs=None):
+        """Advance rays and mean flow in place by nsteps RK3 steps (reference RK3 + rhs_default semantics).
+        _outs = (rr_out, mm_out): the constant-N column step writes the new rr, mm there instead (advance())."""
         eng = self.eng
         p = self.params(dt)
         g = eng.grid_struct(self.grid_devs)
-        column = not p.hprop and not p.saturate_online and len(self.grid_devs) == 4 and self.G <= eng.column_max_levels()
+        column = self._is_column(p)
+        assert _outs is None or (column and nsteps == 1)
         sharded = self.dist is not None and self.dist.get_world_size() > 1
         column_nz = (not p.hprop and not p.saturate_online and len(self.grid_devs) == 5 and
                      (not sharded or self.exchange is not None) and self.G <= eng.column_nz_max_levels())
@@ -144,22 +150,23 @@ class RayEnsemble:
             rays = self._rays()
             s = eng.stream
             rr, mm = self.field("rr"), self.field("mm")
+            rr_o, mm_o = (rr, mm) if _outs is None else _outs
         for _ in range(nsteps):
             if column:
                 if self.exchange is not None:       # all-reduces fused into the tails of the two sweeps (peer memory)
                     check(lib.msgwam_column_step_p2p(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
-                                                     eng.ptr(rr), eng.ptr(mm), eng.ptr(self._uu2), eng.ptr(self._vv2),
+                                                     eng.ptr(rr_o), eng.ptr(mm_o), eng.ptr(self._uu2), eng.ptr(self._vv2),
                                                      self.exchange.next(2), s), "msgwam_column_step_p2p")
                 elif self.dist is None or self.dist.get_world_size() == 1:
                     check(lib.msgwam_column_step(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
-                                                 eng.ptr(rr), eng.ptr(mm), eng.ptr(self._uu2), eng.ptr(self._vv2), s),
+                                                 eng.ptr(rr_o), eng.ptr(mm_o), eng.ptr(self._uu2), eng.ptr(self._vv2), s),
                           "msgwam_column_step")
                 else:                               # NCCL all-reduces between the kernels
                     check(lib.msgwam_column_pass_a(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work), s),
                           "msgwam_column_pass_a")
                     self._reduce(self.work[:4 * nc])
                     check(lib.msgwam_column_pass_b(p, rays, self.n, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
-                                                   eng.ptr(rr), eng.ptr(mm), s), "msgwam_column_pass_b")
+                                                   eng.ptr(rr_o), eng.ptr(mm_o), s), "msgwam_column_pass_b")
                     self._reduce(self.work[4 * nc:6 * nc])
                     check(lib.msgwam_column_finish(p, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
                                                    eng.ptr(self._uu2), eng.ptr(self._vv2), s), "msgwam_column_finish")
@@ -185,11 +192,30 @@ class RayEnsemble:
         clamp = saturate and not p.saturate_online
         if history is not None and history.count == 0:
             history.record(self, 0)
+        fused_commit = clamp and self._is_column(p)
         for k in range(1, nsteps + 1):
             if clamp:
                 if self._old is None or self._old.shape[1] < self.cap:
                     self._old = eng.empty(3, self.cap)
                 old = self._old[:, :self.n]
+            if fused_commit:
+                # constant-N column step: only rr and mm change.  The step writes them out of place, and the clamp kernel
+                # -- which needs both ends of the step -- copies them into the ray store: no copies of the old state
+                self.step(dt, 1, _outs=(old[0], old[2]))
+                dens, gd = self.field("dens"), self.grid_devs
+                rr, drr, mm = self.field("rr"), self.field("drr"), self.field("mm")
+                check(lib.msgwam_saturation_step_commit(
+                    p, self.n, eng.ptr(dens), eng.ptr(rr), eng.ptr(old[0]), eng.ptr(drr), eng.ptr(drr),
+                    eng.ptr(self.field("kk")), eng.ptr(self.field("ll")), eng.ptr(mm), eng.ptr(old[2]),
+                    eng.ptr(self.field("dkk")), eng.ptr(self.field("dll")), eng.ptr(self.field("rr_mm_area")),
+                    eng.ptr(gd[1]), eng.ptr(gd[2]), _vp(0), eng.ptr(dens), eng.ptr(rr), eng.ptr(mm), eng.stream),
+                    "msgwam_saturation_step_commit")
+                eng.launches += 1
+                self.steps_done += 1
+                if history is not None and self.steps_done % history.every == 0:
+                    history.record(self, self.steps_done)
+                continue
+            if clamp:
                 old[0].copy_(self.field("rr")); old[1].copy_(self.field("drr")); old[2].copy_(self.field("mm"))
             self.step(dt)
             if clamp:

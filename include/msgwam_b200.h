@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MSGWAM_ABI_VERSION 3
+#define MSGWAM_ABI_VERSION 4   /* 4: peer inboxes hold 16-byte self-validating cells; msgwam_saturation_step_commit */
 
 #define MSGWAM_E_BADARG      (-1)   /* null pointer / negative size / inconsistent arguments   */
 #define MSGWAM_E_GRID_SIZE   (-2)   /* G too small (< 3) or too large for the fused column kernels */

@@ -92,7 +92,7 @@ SIGNATURES = {
 }
 
 
-ABI_VERSION = 3          # MSGWAM_ABI_VERSION of include/msgwam_b200.h
+ABI_VERSION = 4          # MSGWAM_ABI_VERSION of include/msgwam_b200.h
 
 
 def _load():

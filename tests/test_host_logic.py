@@ -191,3 +191,32 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+
+
+def test_snapshot_params_memo_follows_every_input():
+    """_cabi.snapshot_params memoises on its inputs (the host-buffer RK3 calls it once per step): every input that
+    changes must change the snapshot, and a hit must equal a fresh computation byte for byte."""
+    from msgwam_b200 import _cabi
+    g = np.linspace(0.0, 100e3, 101)
+    gs = .5 * (g[:-1] + g[1:])
+    base = dict(bvf=0.01, phi0=0.3, kappa=1.0, saturate_online=False, hprop=False, grid=g, grids=gs)
+
+    def fresh(dt, kw):
+        return bytes(_cabi._snapshot_uncached(dt, kw["bvf"], kw["phi0"], kw["kappa"], kw["saturate_online"], kw["hprop"],
+                                              kw["grid"], kw["grids"], _cabi.ROT_EARTH_DEFAULT, _cabi.RAD_EARTH_DEFAULT))
+
+    assert bytes(_cabi.snapshot_params(120.0, **base)) == fresh(120.0, base)
+    assert bytes(_cabi.snapshot_params(120.0, **base)) == fresh(120.0, base)          # the memo hit
+    for name, value in (("bvf", 0.02), ("phi0", -0.3), ("phi0", -0.0), ("kappa", 2.0), ("saturate_online", True),
+                        ("hprop", True), ("grid", g * 2), ("grids", gs[:50])):
+        kw = dict(base, **{name: value})
+        assert bytes(_cabi.snapshot_params(120.0, **kw)) == fresh(120.0, kw), name
+        assert bytes(_cabi.snapshot_params(60.0, **kw)) == fresh(60.0, kw), name
+    # +0.0 and -0.0 latitudes are different inputs (the sign of f0 follows)
+    a = _cabi.snapshot_params(120.0, **dict(base, phi0=0.0))
+    b = _cabi.snapshot_params(120.0, **dict(base, phi0=-0.0))
+    assert np.signbit(b.f0) and not np.signbit(a.f0)
+    # a profile-valued bvf (extension) is only looked at for its rank
+    prof = np.full(gs.shape, 0.01)
+    assert np.isnan(_cabi.snapshot_params(120.0, **dict(base, bvf=prof)).n2)
+    assert _cabi.snapshot_params(120.0, **base).n2 == 0.01 ** 2

@@ -75,8 +75,14 @@ __device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9]
     const double lam = a.r.lam ? a.r.lam[i] : 0.0;
     const double dens = a.r.dens[i], phi = a.r.phi[i], rr = a.r.rr[i], drr = a.r.drr[i];
     const double kk = a.r.kk[i], ll = a.r.ll[i], mm = a.r.mm[i], dmm = a.r.dmm[i];
-    const double sphi = sin(phi), cphi = cos(phi);
-    const double ff = mul(p.two_rot, sphi), f2 = mul(ff, ff);
+    // HPROP off: phi does not move, so an ensemble's derived static ff = 2 Omega sin(phi) (msgwam_derive_statics, the same
+    // expression) stands in for the two trigonometric calls per ray and stage; lam_st, phi_st are then exact zeros
+    // (L:638-639: zeros / (RAD + rr) / cos(phi))
+    const bool use_ff = !p.hprop && a.r.ff != nullptr;
+    double sphi = 0.0, cphi = 1.0, ff;
+    if (use_ff) ff = a.r.ff[i];
+    else { sphi = sin(phi); cphi = cos(phi); ff = mul(p.two_rot, sphi); }
+    const double f2 = mul(ff, ff);
     const double kh2 = add(mul(kk, kk), mul(ll, ll)), m2 = mul(mm, mm);
     const double vk = add(kh2, m2);
     const double n2 = n2_at(a.bvf, a.grids, G, p.inv_dz_grids, p.n2, rr);     // ext: N^2 at the ray centre
@@ -130,8 +136,8 @@ __device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9]
     }
     x[0] = dens; x[1] = lam; x[2] = phi; x[3] = rr; x[4] = drr; x[5] = kk; x[6] = ll; x[7] = mm; x[8] = dmm;
     t[0] = mul(p.saturate_online ? 1.0 : 0.0, st);                            // L:647
-    t[1] = dvd(dvd(cgl, rad), cphi);                                          // L:638
-    t[2] = dvd(cgp, rad);                                                     // L:639
+    t[1] = use_ff ? 0.0 : dvd(dvd(cgl, rad), cphi);                           // L:638
+    t[2] = use_ff ? 0.0 : dvd(cgp, rad);                                      // L:639
     t[3] = drr_st;
     t[4] = ddrr_st;
     t[5] = dkk_st;

@@ -238,7 +238,7 @@ class Engine:
         self.launches += 3
         return tend, du, dv, proj
 
-    def rk3_general(self, p: Params, state, statics, uu, vv, grid_devs, reduce_fn=None, in_place=False):
+    def rk3_general(self, p: Params, state, statics, uu, vv, grid_devs, reduce_fn=None, in_place=False, ff=None):
         """RK3 with rhs_default for any mode: per stage one fused ray sweep (rhs + deposit + low-storage update,
         msgwam_rk_stage_rays), the all-reduce of the deposit when sharded, and the one-CTA mean-flow stage
         (msgwam_rk_stage_grid) -- six launches per step.  in_place: overwrite `state` instead of allocating."""
@@ -258,6 +258,8 @@ class Engine:
                 setattr(rays, k, t.data_ptr())
             for k, t in zip(("dkk", "dll", "rr_mm_area"), statics):
                 setattr(rays, k, t.data_ptr())
+            if ff is not None and not p.hprop:          # 2 Omega sin(phi) of the (fixed) latitudes, see ray_rhs
+                rays.ff = ff.data_ptr()
             check(lib.msgwam_rk_stage_rays(stage, p, rays, n, g, self.ptr(uu), self.ptr(vv), qp, xop, self.ptr(proj), s),
                   "msgwam_rk_stage_rays")
             if reduce_fn is not None:

@@ -176,7 +176,8 @@ class RayEnsemble:
             else:
                 state = [self.field(nm) for nm in STATE]
                 st = [self.field(nm) for nm in STATICS]
-                x, uu, vv = eng.rk3_general(p, state, st, self.uu, self.vv, self.grid_devs, self._reduce, in_place=True)
+                x, uu, vv = eng.rk3_general(p, state, st, self.uu, self.vv, self.grid_devs, self._reduce, in_place=True,
+                                            ff=self.field("ff"))
                 self.uu, self.vv = uu, vv
                 if p.hprop:
                     self._derive()                  # phi moved: ff = 2 Omega sin(phi) for the column kernels

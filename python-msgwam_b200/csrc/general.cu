@@ -348,6 +348,18 @@ __global__ void __launch_bounds__(NT, 3) stage_rays_kernel(const StageArgs a)
         int nlow = 0, nup = 0;
         bool ok = false;
         double x[9], t[9];
+        if (i + 32 < end) {
+            // the next iteration's lines into L2: the sweep waited on its own loads (ncu: 8.9 stall cycles per issue
+            // on the long scoreboard with 24 warps per SM)
+            const msgwam_rays_t &rs = a.r.r;
+            const double *in[12] = {rs.dens, rs.lam, rs.phi, rs.rr, rs.drr, rs.kk, rs.ll, rs.mm, rs.dmm, rs.dkk, rs.dll, rs.rr_mm_area};
+#pragma unroll
+            for (int f = 0; f < 12; ++f) if (in[f]) asm volatile("prefetch.global.L2 [%0];" ::"l"(in[f] + i + 32));
+            if (a.stage != 0) {
+#pragma unroll
+                for (int f = 0; f < 9; ++f) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.q[f] + i + 32));
+            }
+        }
         if (live) {
             ray_rhs(a.r, i, x, t, p.saturate_online != 0);
             // wave_projection(var = 0) of the same state, called as L:654-658

@@ -306,6 +306,9 @@ __global__ void rk_update_kernel(int stage, double dt, const double *__restrict_
 // rhs_default on state x_s (ray_rhs), its deposit (wave_projection var = 0 of the same state, L:653-658) and the
 // low-storage update of all nine ray slots (L:693-698) in one sweep: 9 + 3 + 9 fields read, 9 + 9 written, instead
 // of the rhs / projection / 9 x rk_update kernels (~1.9 KB/ray-step of traffic and ~45 launches per step).
+#ifndef MSGWAM_STAGE_CTAS
+#define MSGWAM_STAGE_CTAS 3
+#endif
 struct StageArgs {
     RhsArgs r;                  // state in, statics, grid fields, uu_s, vv_s
     int stage;
@@ -316,7 +319,7 @@ struct StageArgs {
 };
 
 // dynamic shared memory: warp windows | grids copy | CTA histogram (when they fit), as in project_kernel
-__global__ void __launch_bounds__(NT, 3) stage_rays_kernel(const StageArgs a)
+__global__ void __launch_bounds__(NT, MSGWAM_STAGE_CTAS) stage_rays_kernel(const StageArgs a)
 {
     extern __shared__ double sm[];
     const msgwam_params_t &p = a.r.p;
@@ -648,7 +651,7 @@ int msgwam_rk_stage_rays(int32_t stage, const msgwam_params_t *p, const msgwam_r
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    stage_rays_kernel<<<grid_for(n, NT * 8, 3), NT, a.use_smem ? full : win_bytes, (cudaStream_t)stream>>>(a);
+    stage_rays_kernel<<<grid_for(n, NT * 8, MSGWAM_STAGE_CTAS), NT, a.use_smem ? full : win_bytes, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

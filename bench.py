@@ -1,21 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- ray-steps/s of the RK3 + flux-deposition hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rays R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rays R] [--workload c2|c1]
 
-A "step" is one lprop.RK3 step (3 RK stages, 3 flux depositions, mean-flow update) over the
-synthetic column ensemble of BASELINE.json configs[1]: R = 1e6 ray volumes per GPU, constant N,
-zero mean wind.  One JSON line is printed by rank 0.
+A "step" is one lprop.RK3 step (3 RK stages, 3 flux depositions, mean-flow update) over a synthetic column
+ensemble.  Default workload: BASELINE.json configs[2] physics -- N^2(z) profile, sheared
+U(z), G = 1000 -- at 1.25e7 ray volumes per GPU (8 GPUs = the 1e8 rays of configs[3]), advanced IN PLACE; the timed
+steps follow >= 30 in-place warm-up steps, so the ensemble is in the dispersed steady state every long run lives in.
+One JSON line is printed by rank 0.
 
-  value     device-resident throughput: inputs already in HBM, per-step CUDA-event timing on the launch
-            stream, L2 flushed (256 MiB write) between timed steps, max over ranks.
-  e2e       the same step through the reference-facing call lprop.RK3(dt, var) with HOST (pinned) numpy
-            buffers: H2D of the step's inputs + kernels + D2H of rr, mm, uu, vv inside the timed region.
-  roofline  dominant kernel (pass B: 3 RK stages + 1 deposit + store) against the measured HBM peak.
-  cpu_baseline  the oracle port (C restatement of the reference, 1 thread) on this box's host cores.
+  value     device-resident throughput: state in HBM, K in-place steps timed with CUDA events on the launch stream
+            between barriers, max over ranks (the per-GPU state, 1.4 GB, is far larger than L2).
+  e2e       the same step through the reference-facing call lprop.RK3(dt, var) with HOST numpy buffers
+            (page-locked, statics frozen): H2D of the step's inputs + kernels + D2H of the changed slots inside
+            the timed region; `e2e.pageable` is the same call with ordinary pageable arrays and default statics
+            semantics -- what an unmodified driver script gets.
+  parity    computed in this process at the same N ranks before anything is timed: 2e5 rays (sharded), 3 steps, the
+            CUDA path against the CPU oracle on rank 0; a failure exits non-zero.
+  roofline  dominant kernel against the measured HBM peak (algorithmic bytes per launch / live CUDA-event duration),
+            the whole step beside it, and the fp64-pipe fraction (the sweeps are fp64-issue bound, not HBM bound).
+  configs   (N = 1) the other BASELINE configurations as extra keys: configs[1] (1e6 rays, constant N, zero wind;
+            ordered out-of-place as in round 1, dispersed in place, shuffled, the driver loop `advance`), a
+            configs[4] deletion cycle, and the HPROP / online-saturation regimes.
+  cpu_baseline  the oracle port (C restatement of the reference) on this box's host cores, bounded sample.
 
---impl reference times the reference's CPU algorithm (the oracle port; the reference itself is Python
-and cannot travel to the GPU box) with all host threads on the same workload.
+--impl reference times the reference's CPU algorithm (the oracle port; the reference itself is Python and cannot
+travel to the GPU box) with all host threads on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -34,14 +44,42 @@ import numpy as np  # noqa: E402
 
 METRIC = "ray-steps/sec (RK step incl. flux deposition)"
 UNIT = "ray-steps/s"
-A_STEP = 96.0      # algorithmic B/ray-step, SURVEY.md 8(d): 10 fp64 fields read once + rr, mm written once
-A_PASS_A = 72.0    # pass A: 9 fields read (dens, ff, rr, drr, kk, ll, mm, dmm, dkk*dll); its 24 B/ray hand-over to pass B
-                   # (stage-1 increments, cg_rr(r1)) is implementation traffic, not algorithmic
-A_PASS_B = 88.0    # pass B: the same 9 fields read + rr, mm written (+ the 24 B/ray hand-over read back)
-# dram__bytes_read.sum + dram__bytes_write.sum per ray from the committed `ncu --set full` capture at 1e6 rays
-# (profiles/r01d_column_pass_ncu_full_summary.json): pass A 72.1 + 5.5 MB, pass B 96.2 + 5.5 MB
-NCU_TRAFFIC_PER_RAY = {"A": 79.9, "B": 102.8}
-NCU_TRAFFIC_SOURCE = "ncu --set full at 1e6 rays, profiles/r01d_column_pass_ncu_full_summary.json"
+# algorithmic bytes per ray (every per-ray fp64 field that must be read once + every field that changes
+# written once; hand-over traffic between the two sweeps is implementation traffic and is NOT counted)
+ALG = {
+    "c1": {"step": 96.0, "A": 72.0, "B": 88.0},      # constant N: 10 fields read, rr, mm written
+    "c2": {"step": 112.0, "A": 72.0, "B": 104.0},    # N(z): 10 fields read, rr, drr, mm, dmm written
+}
+# per-ray dram__bytes_read.sum + dram__bytes_write.sum and fp64-pipe utilisation from the committed ncu --set full
+# captures (profiles/): used for roofline.traffic and roofline.fp64 (a profiler number is never a bench value; these
+# only scale the live CUDA-event durations)
+NCU = {
+    "c1": {"A": {"traffic_per_ray": 79.9, "fp64_frac": 0.369, "us_per_mray": 41.0},
+           "B": {"traffic_per_ray": 102.8, "fp64_frac": 0.304, "us_per_mray": 38.3},
+           "source": "profiles/r01d_column_pass_ncu_full_summary.json (1e6 rays, ordered)"},
+    "c2": {"A": {"traffic_per_ray": 116.0, "fp64_frac": 0.265, "us_per_mray": 111.7},
+           "B": {"traffic_per_ray": 151.2, "fp64_frac": 0.284, "us_per_mray": 73.2},
+           "source": "profiles/r02a_nz_dispersed_ncu_full_summary.json (3e6 rays, dispersed)"},
+}
+# one fp64 warp instruction per 2.1 cycles per SM sub-partition, 4 per SM, 148 SMs (profiles/r01_fp64_pipe_microbench.txt)
+FP64_PEAK_SOURCE = "measured DFMA issue rate, tools/micro/fp64_lat.cu (1 warp instruction / 2.1 cycles / SMSP) x 592 SMSPs x SM clock"
+WORKLOADS = {
+    "c2": "configs[2] physics: N^2(z) profile, sheared U(z), flux deposition on a 1000-level grid, %s ray volumes per GPU (8 GPUs: the 1e8 rays of configs[3]), in-place steady state",
+    "c1": "configs[1]: %s ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000, in-place steady state",
+}
+
+
+def fmt_rays(n):
+    return ("%.3g" % n).replace("e+0", "e").replace("e+", "e")
+
+
+def config_dict(args, world):
+    """identical for both arms (the driver compares it)"""
+    return {"workload": WORKLOADS[args.workload] % fmt_rays(args.rays), "rays_per_gpu": args.rays, "grid_levels": 1000,
+            "dt_s": 120.0, "regime": "in place after >= 30 in-place warm-up steps (dispersed ensemble)",
+            "l2": "per-GPU state (%.2f GB) larger than L2; no flush needed" % (args.rays * 14 * 8 / 1e9),
+            "parallelism": "rays sharded over %d rank(s), contiguous index ranges; sum of the deposited flux over ranks twice per step" % world,
+            "mode": "M1 coupled (reference RK3 semantics: mean flow inside the RK state), 2 ray sweeps per step"}
 
 
 def measured_peaks():
@@ -50,6 +88,14 @@ def measured_peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_threads():
+    """threads the CPU arm may use: the affinity mask, not OMP_NUM_THREADS (torchrun sets that to 1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -63,6 +109,7 @@ class ClockSampler:
         self.proc = None
         self.thread = None
         self.sm, self.mx, self.reasons = [], [], set()
+        self.active = False          # samples are kept only while a timed region is open
         try:
             import threading
             import pynvml
@@ -85,11 +132,12 @@ class ClockSampler:
             def loop():
                 while not self._stop.is_set():
                     try:
-                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                        mask = int(reasons_fn(h))
-                        for nm, bit in self.BITS.items():
-                            if mask & bit:
-                                self.reasons.add(nm)
+                        if self.active:
+                            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                            mask = int(reasons_fn(h))
+                            for nm, bit in self.BITS.items():
+                                if mask & bit:
+                                    self.reasons.add(nm)
                     except Exception:
                         pass
                     self._stop.wait(period_s)
@@ -139,109 +187,99 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
-def make_scenario(n, rank):
+def make_scenario(workload, n, rank, **kw):
     from msgwam_b200 import scenarios
-    return scenarios.column_ensemble(n, seed=1234 + rank, ngrid=1001)
+    if workload == "c2":
+        return scenarios.nz_sheared_ensemble(n, seed=1234 + rank, **kw)
+    return scenarios.column_ensemble(n, seed=1234 + rank, ngrid=1001, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_rate(workload, n_sample, steps, warmup, nthreads, budget_s=30.0):
+    """ray-steps/s of the oracle port on a bounded sample of the workload (in-place stepping, like the GPU arm)"""
+    import oracle
+    sc = make_scenario(workload, n_sample, 0)
+    orc = oracle.Oracle(sc.oracle_cfg(), nthreads=nthreads)
+    var = sc.var()
+    for _ in range(max(warmup, 1)):
+        var = orc.RK3(sc.dt, var)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        var = orc.RK3(sc.dt, var)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return n_sample * done / dt, done, dt
 
 
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the reference algorithm on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    import oracle
-    n = args.rays if args.steps <= 30 else min(args.rays, 250_000)     # bounded sample per step
-    sc = make_scenario(n, 0)
-    best = None
-    tmax = oracle.max_threads()
-    for nthreads in sorted({1, tmax}, reverse=True):
-        orc = oracle.Oracle(sc.oracle_cfg(), nthreads=nthreads)
-        for _ in range(max(args.warmup, 1) if nthreads == tmax else 1):
-            orc.RK3(sc.dt, sc.var())
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            orc.RK3(sc.dt, sc.var())
-        dt = time.perf_counter() - t0
-        rate = n * args.steps / dt
-        if best is None or rate > best[0]:
-            best = (rate, nthreads, dt)
-    rate, cores, dt = best
+    threads = host_threads()
+    n = min(args.rays, 500_000 if args.workload == "c2" else 1_000_000)       # bounded sample per step
+    steps = min(args.steps, 20)
+    rate, done, dt = oracle_rate(args.workload, n, steps, min(args.warmup, 2), threads, budget_s=60.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": ("configs[1]: 1e6 ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000" if args.rays == 1_000_000 else
-                                "configs[1] ensemble at %d ray volumes per GPU (--rays), 1-D column, constant N, zero mean wind, G=1000" % args.rays),
-                   "rays_per_gpu": args.rays, "grid_levels": 1000, "dt_s": sc.dt,
-                   "sample": "each timed step advances a bounded sample of %d rays of that ensemble on the host cores" % n},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "oracle/msgwam_oracle.c (C restatement of lib/libprop.py RK3+rhs_default+wave_projection; the "
-                                   "Python reference cannot run on the GPU box and does ~2.3e4 ray-steps/s, BASELINE.md) on %d rays per step, "
-                                   "%d steps, best of {1,%d} OpenMP threads" % (n, args.steps, tmax)},
+        "config": config_dict(args, world),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "oracle/msgwam_oracle.c (C restatement of lib/libprop.py RK3 + rhs_default + wave_projection; the "
+                                   "Python reference cannot run on the GPU box and does ~2.3e4 ray-steps/s, BASELINE.md) on %d rays of the "
+                                   "workload per step, %d in-place steps in %.1f s, %d OpenMP threads (affinity mask)" % (n, done, dt, threads)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def bind_numa(local_rank):
+    """keep this rank's host threads (and the pages they touch) on the CPUs nearest its GPU: the pinned staging buffers
+    of the e2e path then sit on the right socket.  NVML knows the affinity; failures are ignored."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, local_rank, world):
+    numa_cpus = bind_numa(local_rank) if world > 1 else None
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import msgwam_b200.libprop as lprop
+    from msgwam_b200 import scenarios
     from msgwam_b200._engine import Engine
     from msgwam_b200._cabi import check, lib
+    from msgwam_b200.distributed import PeerExchange, rk3_host_sharded, shard_range
     from msgwam_b200.ensemble import RayEnsemble
 
-    n = args.rays
-    sc = make_scenario(n, rank)
-    sc.install(lprop)
     eng = Engine.get()
     dev = eng.device
-    ens = RayEnsemble.from_scenario(sc)
-    p = ens.params(sc.dt)
-    g = eng.grid_struct(ens.grid_devs)
-    rays = ens._rays()
-    rr_out, mm_out = eng.empty(n), eng.empty(n)
-    uu_out, vv_out = eng.empty(ens.G), eng.empty(ens.G)
-    nc = ens.G - 1
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     P = eng.ptr
-
-    from msgwam_b200.distributed import PeerExchange
-    exchange = PeerExchange.get(ens.G) if world > 1 else None
-
-    def reduce_(t):
-        if world > 1 and exchange is None:
-            dist.all_reduce(t)
-
-    def pass_a():
-        check(lib.msgwam_column_pass_a(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), eng.stream), "pass_a")
-
-    def pass_b():
-        if exchange is not None:      # chain kernel all-reduces D0|D1 over peer memory, then the sweep
-            check(lib.msgwam_column_pass_b_p2p(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out),
-                                               exchange.next(), eng.stream), "pass_b_p2p")
-        else:
-            check(lib.msgwam_column_pass_b(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out), eng.stream), "pass_b")
-
-    def finish():
-        if exchange is not None:
-            check(lib.msgwam_column_finish_p2p(p, g, P(ens.uu), P(ens.vv), P(ens.work), P(uu_out), P(vv_out), exchange.next(),
-                                               eng.stream), "finish_p2p")
-        else:
-            check(lib.msgwam_column_finish(p, g, P(ens.uu), P(ens.vv), P(ens.work), P(uu_out), P(vv_out), eng.stream), "finish")
-
-    def step():          # out of place: every timed step does identical work on the same input state
-        if world == 1:   # the call libprop.RK3 / RayEnsemble.step make on one GPU: two launches, finish fused as pass B's tail
-            check(lib.msgwam_column_step(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out),
-                                         P(uu_out), P(vv_out), eng.stream), "column_step")
-        elif exchange is not None:   # several GPUs: still two launches; the all-reduces run in the sweeps' tails over NVLink
-            check(lib.msgwam_column_step_p2p(p, rays, n, g, P(ens.uu), P(ens.vv), P(ens.work), P(rr_out), P(mm_out),
-                                             P(uu_out), P(vv_out), exchange.next(2), eng.stream), "column_step_p2p")
-        else:                        # NCCL fallback: all-reduces between the kernels
-            pass_a(); reduce_(ens.work[:4 * nc]); pass_b(); reduce_(ens.work[4 * nc:6 * nc]); finish()
+    wl = args.workload
+    n = args.rays
 
     def barrier():
         torch.cuda.synchronize()
@@ -249,177 +287,211 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_(); step()
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- parity at this number of ranks, before anything is timed ---------------------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(args, rank, world, dist if world > 1 else None)
+        if rank == 0 and not parity["ok"]:
+            print(json.dumps({"metric": METRIC, "error": "parity check failed", "parity": parity, "n_gpus": world}), flush=True)
+        if not parity["ok"]:
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(1)
+
+    # ---- the workload, resident in HBM --------------------------------------------------------------------------
+    sc = make_scenario(wl, n, rank)
+    ens = RayEnsemble.from_scenario(sc)
+    exchange = ens.exchange
+    dt_s = sc.dt
+    host_state = sc.state           # kept for the e2e leg
+    k_warm = max(args.warmup, 30)
+    ens.step(dt_s, k_warm)
     barrier()
+    ens.check_errors()
     try:
         uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         uuid = None
     sampler = ClockSampler(local_rank, uuid) if rank == 0 else None
 
-    # ---- value: device-resident steps, per-step events, L2 flushed between steps ------------------
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- value: K in-place steps between barriers, device time, max over ranks --------------------------------
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    if sampler:
+        sampler.active = True
     wall0 = time.perf_counter()
-    for a, b in evs:
-        flush.zero_()
-        a.record(); step(); b.record()
+    ev0.record()
+    for a, b in per:
+        a.record(); ens.step(dt_s); b.record()
+    ev1.record()
     barrier()
     wall = time.perf_counter() - wall0
-    t_steps = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
-    tt = torch.tensor([t_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_steps = float(tt.item())
-    launches = (2 if (world == 1 or exchange is not None) else 3) * args.steps
+    if sampler:
+        sampler.active = False
+    t_steps = maxr(ev0.elapsed_time(ev1) * 1e-3)
+    per_ms = [a.elapsed_time(b) for a, b in per]
+    launches = eng.launches - launches0
+    ens.check_errors()                                      # the peer exchange's error word must be clean
+    finite = bool(torch.isfinite(ens.uu).all() and torch.isfinite(ens.field("rr")).all() and torch.isfinite(ens.field("mm")).all())
 
-    # ---- per-kernel timing for the roofline (single rank's kernels; no collectives inside) --------
-    ka, kb, kf = [], [], []
-    flush.zero_(); pass_a(); reduce_(ens.work[:4 * nc]); pass_b(); reduce_(ens.work[4 * nc:6 * nc]); finish()   # first launch of the split-form kernels
+    # ---- per-kernel durations for the roofline: an event between the two launches of a step ---------------------
+    # (separate loop: the event record between the sweeps defeats the programmatic overlap of pass B's prologue with
+    # pass A's tail, so the two durations add up to a little more than a fused step)
+    mid, e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    for e in (mid, e0, e1):
+        e.record()
     torch.cuda.synchronize()
-    for _ in range(max(3, min(args.steps, 20))):
-        flush.zero_()
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        e[0].record(); pass_a(); e[1].record(); reduce_(ens.work[:4 * nc]); pass_b_start = torch.cuda.Event(enable_timing=True)
-        pass_b_start.record(); pass_b(); e[2].record(); reduce_(ens.work[4 * nc:6 * nc]); fin0 = torch.cuda.Event(enable_timing=True)
-        fin0.record(); finish(); e[3].record()
+    ka, kb = [], []
+    for _ in range(max(3, min(args.steps, 10))):
+        barrier()
+        check(lib.msgwam_debug_mid_event(mid.cuda_event), "msgwam_debug_mid_event")
+        e0.record(); ens.step(dt_s); e1.record()
+        check(lib.msgwam_debug_mid_event(None), "msgwam_debug_mid_event")
         torch.cuda.synchronize()
-        ka.append(e[0].elapsed_time(e[1])); kb.append(pass_b_start.elapsed_time(e[2])); kf.append(fin0.elapsed_time(e[3]))
-    t_a, t_b, t_f = (statistics.mean(x) * 1e-3 for x in (ka, kb, kf))     # average launch duration, as the contract asks
+        ka.append(e0.elapsed_time(mid)); kb.append(mid.elapsed_time(e1))
+    t_a, t_b = maxr(statistics.mean(ka) * 1e-3), maxr(statistics.mean(kb) * 1e-3)
+    ens.check_errors()
 
-    # ---- e2e: the reference-facing call with host buffers ------------------------------------------
+    # ---- e2e: the reference-facing call with host buffers --------------------------------------------------------
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
         t.numpy()[...] = a
         return t
-    keep = [pinned(np.ascontiguousarray(a)) for a in list(sc.state) + [sc.uu, sc.vv, sc.dkk, sc.dll, sc.rr_mm_area]]
-    var = np.empty(11, dtype=object)
-    for i in range(11):
-        var[i] = keep[i].numpy()
-    lprop.set_statics(dkk=keep[11].numpy(), dll=keep[12].numpy(), rr_mm_area=keep[13].numpy())
-    # per step: dens, phi, rr, drr, kk, ll, mm, dmm + grid fields (the per-run statics dkk, dll are uploaded by the
-    # first call only, as long as the caller keeps passing the same arrays)
-    h2d = 8 * n * 8 + (ens.G + 1 + 6 * ens.G) * 8
-    d2h = 2 * n * 8 + 2 * ens.G * 8                          # rr, mm, uu, vv
+    sc.install(lprop)
+    G = ens.G
+    nz = wl == "c2"
+    n_up = 8                                                 # dens, phi, rr, drr, kk, ll, mm, dmm (lam stays on the host)
+    n_down = 4 if nz else 2                                  # rr, mm (+ drr, dmm with N(z))
+    grid_bytes = (G + 1 + 6 * G + (G if nz else 0)) * 8
     if world == 1:
-        def e2e_step():
-            return lprop.RK3(sc.dt, var)
+        def e2e_step(v):
+            return lprop.RK3(dt_s, v)
     else:
-        from msgwam_b200.distributed import rk3_host_sharded
-        def e2e_step():
-            return rk3_host_sharded(lprop, sc.dt, var)
-    k_e2e = max(3, min(args.steps, 10))
-    outs = [e2e_step() for _ in range(3)]                    # warm-up; results kept alive so that the pinned result
-    del outs                                                 # buffers of two steps are in the host allocator's cache
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(k_e2e):
-        out = e2e_step()
-        _ = float(out[9][0])                                 # the step's result is read on the host
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    t_e2e = float(te.item())
-    # ---- the same step in the other regimes of the deposit (N = 1; reported beside the headline, not part of it) ----
-    regimes = None
-    if world == 1 and not args.no_regimes:
-        def time_steps(e2, k, in_place):
-            pp, gg, rr_ = e2.params(sc.dt), eng.grid_struct(e2.grid_devs), e2._rays()
-            r_o, m_o = (e2.field("rr"), e2.field("mm")) if in_place else (rr_out, mm_out)
-            ts = []
-            for _ in range(k):
-                flush.zero_()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                check(lib.msgwam_column_step(pp, rr_, n, gg, P(e2.uu), P(e2.vv), P(e2.work), P(r_o), P(m_o),
-                                             P(e2._uu2), P(e2._vv2), eng.stream), "column_step")
-                b.record()
-                if in_place:
-                    e2.uu, e2._uu2 = e2._uu2, e2.uu
-                    e2.vv, e2._vv2 = e2._vv2, e2.vv
-                ts.append((a, b))
-            torch.cuda.synchronize()
-            return statistics.median(a.elapsed_time(b) for a, b in ts) * 1e-3
-        from msgwam_b200 import scenarios as _scn
-        k_r = max(5, min(args.steps, 20))
-        ens_d = RayEnsemble.from_scenario(sc)
-        time_steps(ens_d, 30, True)                              # the ensemble disperses within ~10 in-place steps
-        t_disp = time_steps(ens_d, k_r, True)
-        sc_s = _scn.column_ensemble(n, seed=1234 + rank, ngrid=1001, shuffled=True)
-        ens_s = RayEnsemble.from_scenario(sc_s)
-        time_steps(ens_s, 3, False)
-        t_shuf = time_steps(ens_s, k_r, False)
-        regimes = {"note": "median GPU time per step, L2 flushed; the headline times the height-ordered ensemble of SURVEY 8(d)",
-                   "dispersed_after_30_in_place_steps": {"ms_per_step": t_disp * 1e3, "value": n / t_disp, "unit": UNIT},
-                   "shuffled_ray_order": {"ms_per_step": t_shuf * 1e3, "value": n / t_shuf, "unit": UNIT}}
-        del ens_d, ens_s
-    clocks = sampler.stop() if sampler else None
+        def e2e_step(v):
+            return rk3_host_sharded(lprop, dt_s, v)
 
+    def e2e_leg(pin, frozen, k):
+        arrs = list(host_state) + [sc.uu, sc.vv, sc.dkk, sc.dll, sc.rr_mm_area]
+        keep = [pinned(np.ascontiguousarray(a)) for a in arrs] if pin else None
+        host = [t.numpy() for t in keep] if pin else [np.array(a, dtype=np.float64) for a in arrs]
+        var = np.empty(11, dtype=object)
+        for i in range(11):
+            var[i] = host[i]
+        lprop.set_statics(dkk=host[11], dll=host[12], rr_mm_area=host[13])
+        lprop.freeze_statics(frozen)
+        outs = [e2e_step(var) for _ in range(2)]             # warm-up (result buffers enter the pinned allocator's cache)
+        del outs
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            out = e2e_step(var)
+            _ = float(out[9][0])                             # the step's result is read on the host
+        torch.cuda.synchronize()
+        t = maxr(time.perf_counter() - t0)
+        lprop.freeze_statics(False)
+        h2d = (n_up + (0 if frozen else 2)) * n * 8 + grid_bytes
+        d2h = n_down * n * 8 + 2 * G * 8
+        return {"value": n * world * k / t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k,
+                "ms_per_step": t / k * 1e3}
+    k_e2e = max(3, min(args.steps, 5 if n > 4_000_000 else 10))
+    if sampler:
+        sampler.active = True
+    e2e = e2e_leg(True, True, k_e2e)
+    e2e["api"] = ("msgwam_b200.libprop.RK3(dt, var)" if world == 1 else "msgwam_b200.distributed.rk3_host_sharded(lprop, dt, var) (lprop.RK3 on this rank's slice)") + \
+        " with page-locked numpy buffers, statics frozen (lprop.freeze_statics())"
+    if sampler:
+        sampler.active = False
+    e2e_page = None
+    if not args.no_extras:
+        e2e_page = e2e_leg(False, False, max(2, k_e2e // 2))
+        e2e_page["api"] = "the same call with ordinary pageable numpy arrays and the default statics semantics (dkk, dll uploaded every call): what an unmodified driver script gets"
+        e2e["pageable"] = e2e_page
+    del host_state
+
+    # ---- the other BASELINE configurations and regimes (N = 1; reported beside the headline) --------------------
+    extras = None
+    if world == 1 and not args.no_extras:
+        del ens
+        torch.cuda.empty_cache()
+        extras = extra_configs(args, eng, torch)
+    clocks = sampler.stop() if sampler else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------------
+    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        import oracle
-        orc = oracle.Oracle(sc.oracle_cfg(), nthreads=1)
-        orc.RK3(sc.dt, sc.var())
-        t0 = time.perf_counter(); reps = 0
-        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 40):
-            orc.RK3(sc.dt, sc.var()); reps += 1
-        dtc = time.perf_counter() - t0
-        cpu = {"value": n * reps / dtc, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "oracle port (C, 1 thread, -O2, no FMA) on the full %d-ray ensemble, %d RK3 steps in %.1f s; "
-                         "the unmodified Python reference does ~2.3e4 ray-steps/s on one core (BASELINE.md)" % (n, reps, dtc),
-               "host_cpus": os.cpu_count()}
+        threads = host_threads()
+        ns = min(n, 500_000 if wl == "c2" else 1_000_000)
+        r1, d1, s1 = oracle_rate(wl, ns, 4, 1, 1, budget_s=8.0)
+        rt, dn, sn = oracle_rate(wl, ns, 20, 1, threads, budget_s=12.0)
+        cpu = {"value": rt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "oracle port (C, -O2, no FMA contraction) on %d rays of the workload, %d in-place RK3 steps in %.1f s with %d OpenMP "
+                         "threads; one thread: %.3e ray-steps/s; the unmodified Python reference does ~2.3e4 on one core (BASELINE.md)" % (
+                             ns, dn, sn, threads, r1),
+               "one_thread": r1, "host_cpus": os.cpu_count()}
 
     peak, peak_src = measured_peaks()
     total_rays = n * world
     value = total_rays * args.steps / t_steps
-    kernels = {
-        "A": {"name": "column_pass<0> (pass A: deposit r0, stage 1, deposit r1, hand-over)", "ms": t_a * 1e3, "alg": A_PASS_A},
-        "B": {"name": "column_pass<1> (pass B: mean-flow chain, stages 2-3, deposit r2, store)", "ms": t_b * 1e3, "alg": A_PASS_B},
-    }
-    dom = "A" if t_a >= t_b else "B"           # the roofline is reported for whichever sweep takes longer
+    names = {"c2": ("column_pass_nz<0> (pass A: deposit r0, stage 1, deposit r1, hand-over)",
+                    "column_pass_nz<1> (pass B: mean-flow chain, stages 2-3, deposit r2, store)"),
+             "c1": ("column_pass<0> (pass A: deposit r0, stage 1, deposit r1, hand-over)",
+                    "column_pass<1> (pass B: mean-flow chain, stages 2-3, deposit r2, store)")}[wl]
+    kern = {"A": {"name": names[0], "ms": t_a * 1e3, "alg": ALG[wl]["A"]}, "B": {"name": names[1], "ms": t_b * 1e3, "alg": ALG[wl]["B"]}}
+    dom = "A" if t_a >= t_b else "B"
     oth = "B" if dom == "A" else "A"
-    ach = kernels[dom]["alg"] * n / (kernels[dom]["ms"] * 1e-3) / 1e9
+    ach = kern[dom]["alg"] * n / (kern[dom]["ms"] * 1e-3) / 1e9
+    clk = (clocks or {}).get("sm_mhz") or 1965.0
+    fp64_peak = 592 / 2.1 * clk * 1e6                        # fp64 warp instructions per second
+    ncu = NCU[wl]
+
+    def fp64_of(k):
+        # fp64-pipe utilisation of the captured launch, rescaled by (captured time per ray / live time per ray)
+        live_us_per_mray = kern[k]["ms"] * 1e3 / (n / 1e6)
+        frac = ncu[k]["fp64_frac"] * ncu[k]["us_per_mray"] / live_us_per_mray
+        return {"achieved": frac * fp64_peak, "peak": fp64_peak, "frac": frac, "unit": "fp64 warp-instructions/s",
+                "source": "%s; utilisation of the ncu capture (%s) rescaled to the live duration" % (FP64_PEAK_SOURCE, ncu["source"])}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": k_warm,
         "ms_per_step": t_steps / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": ("configs[1]: 1e6 ray volumes per GPU, 1-D column, constant N, zero mean wind, G=1000" if n == 1_000_000 else
-                                "configs[1] ensemble at %d ray volumes per GPU (--rays), 1-D column, constant N, zero mean wind, G=1000" % n),
-                   "rays_per_gpu": n, "grid_levels": ens.G, "dt_s": sc.dt, "l2": "flushed between timed steps (256 MiB write)",
-                   "parallelism": "rays sharded, %d rank(s); all-reduce of the deposited flux twice per step (%s)" % (
-                       world, "none needed" if world == 1 else ("one-shot pushes over NVLink peer memory, fused into the tails of the two sweeps" if exchange is not None else "NCCL")),
-                   "mode": "M1 coupled (reference RK3 semantics: mean flow inside the RK state), 2 ray sweeps per step"},
+        "config": config_dict(args, world),
+        "exchange": "none (one rank)" if world == 1 else ("16-byte self-validating cells pushed over NVLink peer memory inside the two sweeps (no collective kernel)" if exchange is not None else "NCCL all-reduce between the kernels"),
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": NCU_TRAFFIC_PER_RAY[dom] * n, "traffic_source": NCU_TRAFFIC_SOURCE,
-                     "kernel": kernels[dom]["name"], "algorithmic_bytes_per_ray": kernels[dom]["alg"],
-                     "kernel_ms": kernels[dom]["ms"], "peak_source": peak_src,
-                     "note": "the sweeps are bound by instruction issue / fp64 latency, not by HBM (ncu: issue slots 59 % busy, "
-                             "fp64 pipe 37 %, DRAM 23 %): see profiles/r01_summary.md",
-                     "other_kernels": {kernels[oth]["name"]: {"ms": kernels[oth]["ms"],
-                                                              "achieved_gbs": kernels[oth]["alg"] * n / (kernels[oth]["ms"] * 1e-3) / 1e9,
-                                                              "algorithmic_bytes_per_ray": kernels[oth]["alg"],
-                                                              "traffic": NCU_TRAFFIC_PER_RAY[oth] * n},
-                                       "column_finish (a separate kernel only in the split form)": {"ms": t_f * 1e3}},
-                     "step": {"algorithmic_bytes_per_ray_step": A_STEP,
-                              "achieved_gbs": A_STEP * total_rays * args.steps / t_steps / 1e9 / world,
-                              "frac": A_STEP * total_rays * args.steps / t_steps / 1e9 / world / peak}},
-        "e2e": {"value": total_rays * k_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": k_e2e, "api": "msgwam_b200.libprop.RK3(dt, var) with pinned numpy buffers"},
+                     "traffic": ncu[dom]["traffic_per_ray"] * n, "traffic_source": "ncu --set full, " + ncu["source"],
+                     "kernel": kern[dom]["name"], "algorithmic_bytes_per_ray": kern[dom]["alg"],
+                     "kernel_ms": kern[dom]["ms"], "peak_source": peak_src,
+                     "fp64": fp64_of(dom),
+                     "note": "the sweeps are bound by fp64 instruction issue and shared-memory latency, not by HBM (see fp64 and profiles/r02_summary.md)",
+                     "other_kernels": {kern[oth]["name"]: {"ms": kern[oth]["ms"], "achieved_gbs": kern[oth]["alg"] * n / (kern[oth]["ms"] * 1e-3) / 1e9,
+                                                           "algorithmic_bytes_per_ray": kern[oth]["alg"],
+                                                           "traffic": ncu[oth]["traffic_per_ray"] * n, "fp64": fp64_of(oth)}},
+                     "step": {"algorithmic_bytes_per_ray_step": ALG[wl]["step"],
+                              "achieved_gbs": ALG[wl]["step"] * n * args.steps / t_steps / 1e9,
+                              "frac": ALG[wl]["step"] * n * args.steps / t_steps / 1e9 / peak}},
+        "e2e": e2e,
+        "parity": parity,
         "gpu_launches": launches,
         "clocks": clocks,
-        "wall_s_timed_region_incl_flush": wall,
+        "step_ms_stats": {"min": min(per_ms), "median": statistics.median(per_ms), "max": max(per_ms), "note": "this rank's per-step event times"},
+        "wall_s_timed_region": wall,
+        "state_finite": finite,
     }
-    if regimes is not None:
-        line["regimes"] = regimes
+    if numa_cpus is not None:
+        line["numa"] = "each rank bound to the %d CPUs nearest its GPU (NVML affinity)" % numa_cpus
+    if extras is not None:
+        line["configs"] = extras
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -427,16 +499,162 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def parity_check(args, rank, world, dist):
+    """CUDA path vs the CPU oracle at this number of ranks: ~2e5 rays of the workload's physics (with a feeding-back
+    amplitude), sharded like the bench, 3 in-place steps; the oracle runs the whole ensemble on rank 0."""
+    import torch
+    from msgwam_b200 import scenarios
+    from msgwam_b200.distributed import shard_range
+    from msgwam_b200.ensemble import RayEnsemble
+    n_tot, nsteps = 200_003, 3
+    if args.workload == "c2":
+        sc = scenarios.nz_sheared_ensemble(n_tot, seed=77, amplitude=0.3)
+    else:
+        sc = scenarios.column_ensemble(n_tot, seed=77, ngrid=1001, sheared=True, amplitude=0.3)
+    b, e = shard_range(sc.n, rank, world)
+    ens = RayEnsemble([a[b:e] for a in sc.state], sc.dkk[b:e], sc.dll[b:e], sc.rr_mm_area[b:e], sc.uu, sc.vv, sc.grid, sc.grids,
+                      sc.rhobar, sc.pressure_gradient, bvf=sc.model["bvf"], phi0=sc.model["phi0"])
+    ens.step(sc.dt, nsteps)
+    mine = ens.to_var()                                       # reads the error word, too
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [mine[i] for i in range(11)])
+    else:
+        gathered = [[mine[i] for i in range(11)]]
+    res = {"ok": True}
+    if rank == 0:
+        import oracle
+        t0 = time.perf_counter()
+        orc = oracle.Oracle(sc.oracle_cfg(), nthreads=host_threads())
+        want = start = sc.var()
+        for _ in range(nsteps):
+            want = orc.RK3(sc.dt, want)
+        ray_err, grid_err = 0.0, 0.0
+        for i in range(11):
+            if i >= 9:
+                scale = max(float(np.max(np.abs(want[i]))), 1e-300)
+                for r in range(world):
+                    grid_err = max(grid_err, float(np.max(np.abs(gathered[r][i] - want[i]))) / scale)
+            else:
+                got = np.concatenate([gathered[r][i] for r in range(world)])
+                # relative to the value or to its change over the run, whichever is larger (slots that pass through zero)
+                scale = np.maximum(np.abs(want[i]), np.abs(want[i] - start[i]))
+                diff = np.abs(got - want[i])
+                ray_err = max(ray_err, float(np.max(np.where(diff == 0, 0.0, diff / np.where(scale == 0, 1.0, scale)))))
+        same = all(np.array_equal(gathered[r][9], gathered[0][9]) and np.array_equal(gathered[r][10], gathered[0][10]) for r in range(1, world))
+        tol_ray, tol_grid = 1e-10, 1e-10
+        res = {"ok": bool(ray_err <= tol_ray and grid_err <= tol_grid and same), "rays": n_tot, "steps": nsteps, "ranks": world,
+               "max_ray_rel_err": ray_err, "max_grid_rel_err": grid_err, "tol_ray": tol_ray, "tol_grid": tol_grid,
+               "mean_flow_identical_on_all_ranks": bool(same),
+               "oracle": "oracle port (pinned bit-for-bit to the Python reference for constant N; the N(z) terms are an extension "
+                         "pinned to an independent numpy restatement), %d threads, %.1f s" % (host_threads(), time.perf_counter() - t0)}
+    if world > 1:
+        flag = torch.tensor([1 if res["ok"] else 0], dtype=torch.int32, device="cuda")
+        dist.broadcast(flag, 0)
+        if rank != 0:
+            res = {"ok": bool(int(flag.item()))}
+    del ens
+    return res
+
+
+def extra_configs(args, eng, torch):
+    """N = 1: BASELINE configs[1] and [4] and the general-mode regimes, median GPU time per step."""
+    import msgwam_b200.libprop as lprop
+    from msgwam_b200 import scenarios
+    from msgwam_b200._cabi import check, lib
+    from msgwam_b200.ensemble import RayEnsemble
+    P = eng.ptr
+    out = {}
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=eng.device)
+
+    def timed(fn, k, flush_l2=True):
+        ts = []
+        for _ in range(k):
+            if flush_l2:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            ts.append((a, b))
+        torch.cuda.synchronize()
+        return statistics.median(a.elapsed_time(b) for a, b in ts) * 1e-3
+
+    def entry(n, t, **kw):
+        return dict({"ms_per_step": t * 1e3, "value": n / t, "unit": UNIT}, **kw)
+
+    k = max(5, min(args.steps, 20))
+    # ---- configs[1]: 1e6 rays, constant N, zero wind (the round-1 headline and its regimes) ----
+    n1 = 1_000_000
+    sc1 = scenarios.column_ensemble(n1, seed=1234, ngrid=1001)
+    e1 = RayEnsemble.from_scenario(sc1)
+    p1, g1, r1 = e1.params(sc1.dt), eng.grid_struct(e1.grid_devs), e1._rays()
+    rr_o, mm_o = eng.empty(n1), eng.empty(n1)
+
+    def oop():
+        check(lib.msgwam_column_step(p1, r1, n1, g1, P(e1.uu), P(e1.vv), P(e1.work), P(rr_o), P(mm_o), P(e1._uu2), P(e1._vv2), eng.stream), "column_step")
+    timed(oop, 5)
+    out["c1_ordered_out_of_place"] = entry(n1, timed(oop, k), note="round-1 headline regime: height-ordered ensemble, same input every step, L2 flushed")
+    e1.step(sc1.dt, 30)
+    out["c1_dispersed_in_place"] = entry(n1, timed(lambda: e1.step(sc1.dt), k), note="after 30 in-place steps, L2 flushed")
+    out["c1_advance"] = entry(n1, timed(lambda: e1.advance(sc1.dt, 1), k), note="driver loop on the device: RK3 + post-step saturation clamp (raytracer.py:175-188), dispersed, L2 flushed")
+    scs = scenarios.column_ensemble(n1, seed=1234, ngrid=1001, shuffled=True)
+    es = RayEnsemble.from_scenario(scs)
+    ps, gs_, rs = es.params(scs.dt), eng.grid_struct(es.grid_devs), es._rays()
+
+    def oop_s():
+        check(lib.msgwam_column_step(ps, rs, n1, gs_, P(es.uu), P(es.vv), P(es.work), P(rr_o), P(mm_o), P(es._uu2), P(es._vv2), eng.stream), "column_step")
+    timed(oop_s, 3)
+    out["c1_shuffled_out_of_place"] = entry(n1, timed(oop_s, k), note="random ray order, L2 flushed")
+    del e1, es
+    # ---- general-mode regimes (SURVEY 8 f4): HPROP on, online saturation on, 1e6 rays ----
+    for key, kw in (("hprop", dict(hprop=True)), ("saturate_online", dict(saturate_online=True))):
+        scg = scenarios.column_ensemble(n1, seed=1234, ngrid=1001, sheared=True, amplitude=0.3, phi0=np.deg2rad(-40.0))
+        if "hprop" in kw:
+            scg.hprop = True
+        else:
+            scg.model = dict(scg.model, saturate_online=True)
+        eg = RayEnsemble.from_scenario(scg)
+        eg.step(scg.dt, 3)
+        out["general_" + key] = entry(n1, timed(lambda: eg.step(scg.dt), max(3, k // 2)), note="stage-by-stage kernels (rhs + deposit + low-storage update per stage), in place, L2 flushed")
+        del eg
+    # ---- configs[4]: critical-level stress case with deletion by stream compaction ----
+    n4 = args.c4_rays
+    t0 = time.perf_counter()
+    sc4 = scenarios.critical_level_ensemble(n4, ngrid=1001, stress=True)
+    e4 = RayEnsemble.from_scenario(sc4)
+    del sc4.state
+    build_s = time.perf_counter() - t0
+    cyc = []
+    for c in range(3):
+        a, b, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        before = e4.n
+        torch.cuda.synchronize()
+        a.record(); e4.step(120.0, 10); b.record()
+        after = e4.compact(120.0, scenarios.M_CRIT_STRESS)
+        c2.record(); torch.cuda.synchronize()
+        ms_s, ms_c = a.elapsed_time(b), b.elapsed_time(c2)
+        cyc.append({"rays_before": before, "survivors": after, "ms_10_steps": ms_s, "ray_steps_per_s": 10 * before / (ms_s * 1e-3),
+                    "ms_compaction": ms_c, "compaction_gbs": 16 * 8 * (before + after) / (ms_c * 1e-3) / 1e9})
+    out["c4_critical_level"] = {"rays": n4, "cycles": cyc, "host_build_s": build_s,
+                                "note": "10 in-place steps, then deletion of rays outside the deposit domain or with |m| >= m_crit (stable compaction of the 16-field store: bytes = 16 fields x 8 B x (rays read + survivors written))"}
+    del e4
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rays", type=int, default=1_000_000, help="ray volumes per GPU")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c1"], help="c2: N^2(z) + sheared wind (default); c1: constant N, zero wind")
+    ap.add_argument("--rays", type=int, default=None, help="ray volumes per GPU (default 1.25e7 for c2, 1e6 for c1)")
+    ap.add_argument("--c4-rays", type=int, default=50_000_000, help="rays of the configs[4] deletion cycle (N = 1 extras)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-regimes", action="store_true", help="skip the dispersed / shuffled ensemble timings (N = 1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other configs / regimes and the pageable e2e leg")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
+    if args.rays is None:
+        args.rays = 12_500_000 if args.workload == "c2" else 1_000_000
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

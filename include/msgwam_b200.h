@@ -171,6 +171,12 @@ int msgwam_column_step_nz(const msgwam_params_t *p, const msgwam_rays_t *rays, i
 int32_t msgwam_column_nz_max_levels(void);
 /* offset (in doubles) inside d_work of the error word set by a timed-out peer exchange (0.0 = ok) */
 int64_t msgwam_column_error_offset(int32_t G);
+/* bound of the device-side polls of the peer exchange in seconds (default 120): a rank that is merely late must
+ * never reach it; when it fires the error word is set and the host binding raises at its next synchronisation */
+int msgwam_set_peer_timeout(double seconds);
+/* measurement hook: while `event` (a cudaEvent_t) is set, every fused column step records it between its two
+ * launches so that the sweeps can be timed separately; NULL switches it off */
+int msgwam_debug_mid_event(void *event);
 
 /* single GPU: two launches -- the mean-flow chain and the finish run as the tails of the sweeps, in the last
  * CTA to retire */
@@ -307,6 +313,17 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n,
                            const double *h_pg,
                            double *h_rr_out, double *h_mm_out, double *h_uu_out, double *h_vv_out,
                            double *d_stage, double *d_work, void *stream);
+/* the same call with the N(z) extension (h_bvf: N on grids, G values): rr, drr, mm, dmm come
+ * back; d_stage holds msgwam_host_stage_doubles_nz(n, G) doubles */
+int64_t msgwam_host_stage_doubles_nz(int64_t n, int32_t G);
+int msgwam_rk3_column_nz_host(const msgwam_params_t *p, int64_t n,
+                              const double *const h_state[9], const double *h_dkk, const double *h_dll,
+                              const double *h_uu, const double *h_vv,
+                              const double *h_grid, const double *h_grids, const double *h_rhobar,
+                              const double *h_pg, const double *h_bvf,
+                              double *h_rr_out, double *h_drr_out, double *h_mm_out, double *h_dmm_out,
+                              double *h_uu_out, double *h_vv_out,
+                              double *d_stage, double *d_work, void *stream);
 
 #ifdef __cplusplus
 }

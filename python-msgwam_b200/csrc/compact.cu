@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(CT) count_kernel(int64_t n, const uint8_t *__r
     int c = 0;
     if (start + ITEMS <= n) {
         const uint4 v = *reinterpret_cast<const uint4 *>(keep + start);     // 16 flags, 16-byte aligned
-        c = __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) + __popc(v.w & 0x01010101u);
+        // a flag byte counts when it is non-zero, exactly as the scalar tail and scatter_kernel read it
+        c = __popc(__vcmpne4(v.x, 0u) & 0x01010101u) + __popc(__vcmpne4(v.y, 0u) & 0x01010101u) +
+            __popc(__vcmpne4(v.z, 0u) & 0x01010101u) + __popc(__vcmpne4(v.w, 0u) & 0x01010101u);
     } else {
         for (int k = 0; k < ITEMS; ++k) if (start + k < n && keep[start + k]) ++c;
     }

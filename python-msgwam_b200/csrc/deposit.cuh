@@ -99,9 +99,36 @@ __device__ __forceinline__ double cell_weight(int c, double rl, double ru, doubl
 // native 32-bit ATOMS.ADD and carries -- exact and 2.5x the lane-add rate of the CAS loop in isolation
 // (tools/micro/smem_atomics.cu), but its conversions and carry chains cost more issue slots than the CAS unit costs
 // time: 198 instead of 145 us per step for a dispersed ensemble.)
+// Fixed-point mode (scale != 0; the CTA histogram of the fused column sweeps): a contribution x is added as the 64-bit
+// integer RN(x * scale), scale a power of two chosen from a bound on the sum of |x| over the CTA's rays so that no
+// accumulator can overflow (column_step.cu: deposit bounds).  Shared memory has native 32-bit integer atomics only
+// (fp64, f32 and 64-bit integer adds are all compare-and-swap loops, ATOMS.CAST.SPIN), so the 64-bit add is an
+// ATOMS.ADD on the low word whose returned old value yields the carry, and one on the high word: 3.9 lane-adds per clock
+// per SM against 0.8-1.5 for the fp64 CAS loop (tools/micro/smem_atomics.cu), independent of how the cells collide.
+// Sums are exact in fixed point, hence independent of the order of the adds; the quantum 1 / scale is below 2^-58 of
+// the bound.  Contributions that do not fit (non-finite, or larger than the bound allows) go to the global deposit as
+// fp64 atomics, unscaled.
 struct SplitTargets {
     double *s0, *s1; int *used;
+    double scale = 0.0;                    // 0: fp64 mode
+    double *g0 = nullptr, *g1 = nullptr;   // fixed-point mode: the global deposit rows, for contributions that do not fit
     __device__ __forceinline__ void mark() const { if (used != nullptr) *used = 1; }
+    // both components of up to two cells in fixed point: the four low-word adds first, then the carries and high words
+    __device__ __forceinline__ void add2_fixed(int c0, double x0, double y0, bool two, int c1, double x1, double y1) const
+    {
+        const long long q0 = __double2ll_rn(x0), q1 = __double2ll_rn(y0), q2 = __double2ll_rn(x1), q3 = __double2ll_rn(y1);
+        unsigned *w0 = reinterpret_cast<unsigned *>(s0 + c0), *w1 = reinterpret_cast<unsigned *>(s1 + c0);
+        unsigned *w2 = reinterpret_cast<unsigned *>(s0 + c1), *w3 = reinterpret_cast<unsigned *>(s1 + c1);
+        const unsigned l0 = (unsigned)q0, l1 = (unsigned)q1, l2 = (unsigned)q2, l3 = (unsigned)q3;
+        const unsigned o0 = atomicAdd(w0, l0), o1 = atomicAdd(w1, l1);
+        unsigned o2 = 0, o3 = 0;
+        if (two) { o2 = atomicAdd(w2, l2); o3 = atomicAdd(w3, l3); }
+        const unsigned h0 = (unsigned)(q0 >> 32) + ((o0 + l0) < l0), h1 = (unsigned)(q1 >> 32) + ((o1 + l1) < l1);
+        const unsigned h2 = (unsigned)(q2 >> 32) + ((o2 + l2) < l2), h3 = (unsigned)(q3 >> 32) + ((o3 + l3) < l3);
+        if (h0) atomicAdd(w0 + 1, h0);
+        if (h1) atomicAdd(w1 + 1, h1);
+        if (two) { if (h2) atomicAdd(w2 + 1, h2); if (h3) atomicAdd(w3 + 1, h3); }
+    }
     __device__ __forceinline__ void add(int c, double x, double y) const { atomicAdd(s0 + c, x); atomicAdd(s1 + c, y); }
     // Two cells at once, optimistically: the four read-add-CAS sequences are issued side by side so that their
     // shared-memory round trips overlap (atomicAdd's own CAS loop serialises them); a CAS that lost against another
@@ -190,6 +217,26 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
         }
     } else if (ok) {
         // outlier lane / unordered rays: add to the CTA histogram directly
+        if (sink.scale != 0.0) {
+            // fixed point: scaling by a power of two commutes with the rounding of t * v, so v is scaled once per ray.
+            // A cell weight is at most psv (1 + 2^-52): the ray fits if psv * |v| * scale stays far below 2^63.
+            const double w0 = mul(v0, sink.scale), w1 = mul(v1, sink.scale);
+            if (mul(psv, add(fabs(w0), fabs(w1))) < 2.0e18) {
+                sink.mark();
+                for (int c = nlow; c < nup; c += 2) {
+                    const bool two = c + 1 < nup;
+                    const int c1 = two ? c + 1 : c;
+                    const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g), t1 = cell_weight(c1, rl, ru, psv, dz, rdz, g);
+                    sink.add2_fixed(c, mul(t0, w0), mul(t0, w1), two, c1, mul(t1, w0), mul(t1, w1));
+                }
+            } else {                                            // non-finite or outsized: fp64 atomics on the global deposit
+                for (int c = nlow; c < nup; ++c) {
+                    const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g);
+                    atomicAdd(sink.g0 + c, mul(t0, v0)); atomicAdd(sink.g1 + c, mul(t0, v1));
+                }
+            }
+            return;
+        }
         sink.mark();
         for (int c = nlow; c < nup; c += 2) {
             const bool two = c + 1 < nup;

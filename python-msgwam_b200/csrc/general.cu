@@ -554,11 +554,7 @@ __global__ void __launch_bounds__(NT) pointwise_kernel(const PwArgs a)
 int g_sms = 0, g_smem = 0;
 int props()
 {
-    if (g_sms == 0) {
-        int rc = msgwam_device_info(&g_sms, &g_smem);
-        if (rc) return rc;
-    }
-    return 0;
+    return msgwam_device_info(&g_sms, &g_smem);      // of the current device (cached per device in column_step.cu)
 }
 
 inline int grid_for(int64_t n, int threads, int per_sm)
@@ -576,7 +572,8 @@ int launch_project(ProjArgs &q, int64_t n, cudaStream_t s)
     const size_t full = win_bytes + (size_t)(q.ng + 2 * (q.ng - 1)) * sizeof(double);
     q.use_smem = full <= (size_t)g_smem;
     const size_t bytes = q.use_smem ? full : win_bytes;
-    static bool configured = false;
+    static bool configured_dev[MW_MAX_DEVICES] = {};       // cudaFuncSetAttribute is per device
+    bool &configured = configured_dev[mw_current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem);
         if (e != cudaSuccess) return (int)e;
@@ -645,7 +642,8 @@ int msgwam_rk_stage_rays(int32_t stage, const msgwam_params_t *p, const msgwam_r
     const size_t win_bytes = ((size_t)(NT / 32) * WIN_DOUBLES + 2) * sizeof(double);
     const size_t full = win_bytes + (size_t)(p->G + 2 * (p->G - 1)) * sizeof(double);
     a.use_smem = full <= (size_t)g_smem;
-    static bool configured = false;
+    static bool configured_dev[MW_MAX_DEVICES] = {};
+    bool &configured = configured_dev[mw_current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(stage_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem);
         if (e != cudaSuccess) return (int)e;

@@ -26,7 +26,8 @@ const char *msgwam_error_string(int code)
 
 static inline int64_t pad32(int64_t n) { return (n + 31) & ~(int64_t)31; }
 
-// Page-locked staging for the grid-sized arguments of msgwam_rk3_column_host (one block per process, grown on demand;
+// Page-locked staging for the grid-sized arguments of msgwam_rk3_column_host (one block per process, portable across
+// the process's devices, grown on demand;
 // every call ends with a stream synchronisation, so no copy is in flight when it is reallocated).
 static double *g_pin = nullptr;
 static size_t g_pin_cap = 0;
@@ -36,7 +37,7 @@ static double *pinned_block(size_t doubles)
         if (g_pin) cudaFreeHost(g_pin);
         g_pin = nullptr; g_pin_cap = 0;
         const size_t cap = doubles < 65536 ? 65536 : doubles;
-        if (cudaHostAlloc(reinterpret_cast<void **>(&g_pin), cap * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&g_pin), cap * sizeof(double), cudaHostAllocPortable) != cudaSuccess) {
             g_pin = nullptr;
             return nullptr;
         }
@@ -45,25 +46,36 @@ static double *pinned_block(size_t doubles)
     return g_pin;
 }
 
+// ray-sized doubles of the staging slab: 10 uploaded ray fields + ff + pkl, then the outputs and the stage-1 hand-over
+// (constant N: rr, mm + 3; N(z) profile: rr, drr, mm, dmm + 7)
+static inline int64_t ray_slots(bool nz) { return nz ? 12 + 4 + 7 : 12 + 2 + 3; }
+
 int64_t msgwam_host_stage_doubles(int64_t n, int32_t G)
 {
     if (n < 0 || G < 3) return 0;
-    // 10 uploaded ray fields + ff + pkl + rr_out + mm_out + 3 of stage-1 hand-over, then grid (G+1), grids, rhobar,
-    // pg (2G), uu, vv, uu_out, vv_out
-    return 17 * pad32(n) + pad32(G + 1) + 8 * pad32(G);
+    // then grid (G+1), grids, rhobar, pg (2G), uu, vv, uu_out, vv_out, (bvf: unused here, keeps one layout)
+    return ray_slots(false) * pad32(n) + pad32(G + 1) + 9 * pad32(G);
 }
 
-int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *const h_state[9], const double *h_dkk,
-                           const double *h_dll, const double *h_uu, const double *h_vv, const double *h_grid,
-                           const double *h_grids, const double *h_rhobar, const double *h_pg, double *h_rr_out,
-                           double *h_mm_out, double *h_uu_out, double *h_vv_out, double *d_stage, double *d_work,
-                           void *stream)
+int64_t msgwam_host_stage_doubles_nz(int64_t n, int32_t G)
 {
+    if (n < 0 || G < 3) return 0;
+    return ray_slots(true) * pad32(n) + pad32(G + 1) + 9 * pad32(G);
+}
+
+// h_bvf != NULL: the N(z) extension (msgwam_column_step_nz; rr, drr, mm, dmm come back), else the reference's scalar N
+static int rk3_column_host_impl(const msgwam_params_t *p, int64_t n, const double *const h_state[9], const double *h_dkk,
+                                const double *h_dll, const double *h_uu, const double *h_vv, const double *h_grid,
+                                const double *h_grids, const double *h_rhobar, const double *h_pg, const double *h_bvf,
+                                double *h_rr_out, double *h_drr_out, double *h_mm_out, double *h_dmm_out, double *h_uu_out,
+                                double *h_vv_out, double *d_stage, double *d_work, void *stream)
+{
+    const bool nz = h_bvf != nullptr;
     if (!p || n < 0 || !h_state || !h_uu || !h_vv || !h_grid || !h_grids || !h_rhobar || !h_pg || !h_uu_out || !h_vv_out ||
         !d_stage || !d_work)
         return MSGWAM_E_BADARG;
     if (p->G < 3) return MSGWAM_E_GRID_SIZE;
-    if (n > 0 && (!h_rr_out || !h_mm_out)) return MSGWAM_E_BADARG;
+    if (n > 0 && (!h_rr_out || !h_mm_out || (nz && (!h_drr_out || !h_dmm_out)))) return MSGWAM_E_BADARG;
     if ((h_dkk == nullptr) != (h_dll == nullptr)) return MSGWAM_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t np = pad32(n), G = p->G, gp = pad32(G);
@@ -71,10 +83,12 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
     // state order: dens, lam, phi, rr, drr, kk, ll, mm, dmm  (lam is not needed on the device)
     double *d_dens = d, *d_phi = d + np, *d_rr = d + 2 * np, *d_drr = d + 3 * np, *d_kk = d + 4 * np, *d_ll = d + 5 * np,
            *d_mm = d + 6 * np, *d_dmm = d + 7 * np, *d_dkk = d + 8 * np, *d_dll = d + 9 * np, *d_ff = d + 10 * np,
-           *d_pkl = d + 11 * np, *d_rro = d + 12 * np, *d_mmo = d + 13 * np, *d_st1 = d + 14 * np;
-    double *g = d + 17 * np;
+           *d_pkl = d + 11 * np, *d_out = d + 12 * np;
+    double *d_rro = d_out, *d_mmo = d_out + np, *d_drro = d_out + 2 * np, *d_dmmo = d_out + 3 * np;   // the last two: N(z) only
+    double *d_st1 = d_out + (nz ? 4 : 2) * np;
+    double *g = d + ray_slots(nz) * np;
     double *d_grid = g, *d_grids = g + pad32(G + 1), *d_rho = d_grids + gp, *d_pg = d_rho + gp, *d_uu = d_pg + 2 * gp,
-           *d_vv = d_uu + gp, *d_uuo = d_vv + gp, *d_vvo = d_uuo + gp;
+           *d_vv = d_uu + gp, *d_bvf = d_vv + gp, *d_uuo = d_bvf + gp, *d_vvo = d_uuo + gp;
     cudaError_t e;
 #define MW_H2D(dst, src, cnt)                                                                          \
     do {                                                                                               \
@@ -87,7 +101,7 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
     // The grid-sized inputs are ordinary (pageable) numpy arrays: six cudaMemcpyAsync calls from pageable memory are
     // six staged, blocking copies (~100 us in all).  They are gathered into one page-locked block laid out like the
     // device region and go up with ONE asynchronous copy; uu, vv and the error word come back the same way.
-    const int64_t gblock = pad32(G + 1) + 6 * gp;                 // grid | grids | rhobar | pg (2) | uu | vv
+    const int64_t gblock = pad32(G + 1) + 7 * gp;                 // grid | grids | rhobar | pg (2) | uu | vv | bvf
     double *pin = pinned_block((size_t)(gblock + 2 * gp + 8));
     if (!pin) return (int)cudaErrorMemoryAllocation;
     {
@@ -97,7 +111,8 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
         memcpy(q, h_rhobar, (size_t)G * sizeof(double)); q += gp;
         memcpy(q, h_pg, (size_t)(2 * G) * sizeof(double)); q += 2 * gp;                  // (2, G) contiguous, as the kernels index it
         memcpy(q, h_uu, (size_t)G * sizeof(double)); q += gp;
-        memcpy(q, h_vv, (size_t)G * sizeof(double));
+        memcpy(q, h_vv, (size_t)G * sizeof(double)); q += gp;
+        if (nz) memcpy(q, h_bvf, (size_t)G * sizeof(double));
     }
     e = cudaMemcpyAsync(d_grid, pin, (size_t)gblock * sizeof(double), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return (int)e;
@@ -111,14 +126,17 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
     msgwam_rays_t r{};
     r.dens = d_dens; r.phi = d_phi; r.rr = d_rr; r.drr = d_drr; r.kk = d_kk; r.ll = d_ll; r.mm = d_mm; r.dmm = d_dmm;
     r.dkk = d_dkk; r.dll = d_dll; r.ff = d_ff; r.pkl = d_pkl; r.stage1 = d_st1;
-    msgwam_grid_t gr{d_grid, d_grids, d_rho, d_pg, nullptr};
-    rc = msgwam_column_step(p, &r, n, &gr, d_uu, d_vv, d_work, d_rro, d_mmo, d_uuo, d_vvo, stream);
+    msgwam_grid_t gr{d_grid, d_grids, d_rho, d_pg, nz ? d_bvf : nullptr};
+    if (nz) rc = msgwam_column_step_nz(p, &r, n, &gr, d_uu, d_vv, d_work, d_rro, d_drro, d_mmo, d_dmmo, d_uuo, d_vvo, nullptr, stream);
+    else rc = msgwam_column_step(p, &r, n, &gr, d_uu, d_vv, d_work, d_rro, d_mmo, d_uuo, d_vvo, stream);
     if (rc) return rc;
     if (n > 0) {
-        e = cudaMemcpyAsync(h_rr_out, d_rro, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaMemcpyAsync(h_mm_out, d_mmo, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) return (int)e;
+        double *const hs[4] = {h_rr_out, h_mm_out, h_drr_out, h_dmm_out};
+        double *const ds[4] = {d_rro, d_mmo, d_drro, d_dmmo};
+        for (int k = 0; k < (nz ? 4 : 2); ++k) {
+            e = cudaMemcpyAsync(hs[k], ds[k], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) return (int)e;
+        }
     }
     double *pin_out = pin + gblock;                               // uu_out | vv_out | error word
     e = cudaMemcpyAsync(pin_out, d_uuo, (size_t)(2 * gp) * sizeof(double), cudaMemcpyDeviceToHost, s);
@@ -137,6 +155,27 @@ int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *co
         return MSGWAM_E_TIMEOUT;
     }
     return 0;
+}
+
+int msgwam_rk3_column_host(const msgwam_params_t *p, int64_t n, const double *const h_state[9], const double *h_dkk,
+                           const double *h_dll, const double *h_uu, const double *h_vv, const double *h_grid,
+                           const double *h_grids, const double *h_rhobar, const double *h_pg, double *h_rr_out,
+                           double *h_mm_out, double *h_uu_out, double *h_vv_out, double *d_stage, double *d_work,
+                           void *stream)
+{
+    return rk3_column_host_impl(p, n, h_state, h_dkk, h_dll, h_uu, h_vv, h_grid, h_grids, h_rhobar, h_pg, nullptr, h_rr_out,
+                                nullptr, h_mm_out, nullptr, h_uu_out, h_vv_out, d_stage, d_work, stream);
+}
+
+int msgwam_rk3_column_nz_host(const msgwam_params_t *p, int64_t n, const double *const h_state[9], const double *h_dkk,
+                              const double *h_dll, const double *h_uu, const double *h_vv, const double *h_grid,
+                              const double *h_grids, const double *h_rhobar, const double *h_pg, const double *h_bvf,
+                              double *h_rr_out, double *h_drr_out, double *h_mm_out, double *h_dmm_out, double *h_uu_out,
+                              double *h_vv_out, double *d_stage, double *d_work, void *stream)
+{
+    if (!h_bvf) return MSGWAM_E_BADARG;
+    return rk3_column_host_impl(p, n, h_state, h_dkk, h_dll, h_uu, h_vv, h_grid, h_grids, h_rhobar, h_pg, h_bvf, h_rr_out,
+                                h_drr_out, h_mm_out, h_dmm_out, h_uu_out, h_vv_out, d_stage, d_work, stream);
 }
 
 }  // extern "C"

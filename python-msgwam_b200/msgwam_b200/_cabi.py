@@ -71,6 +71,8 @@ SIGNATURES = {
     "msgwam_column_step_nz": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 9 + [ctypes.POINTER(Peers), _vp]),
     "msgwam_column_nz_max_levels": (_i32, []),
     "msgwam_column_error_offset": (_i64, [_i32]),
+    "msgwam_set_peer_timeout": (ctypes.c_int, [_dbl]),
+    "msgwam_debug_mid_event": (ctypes.c_int, [_vp]),
     "msgwam_column_step": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_debug_cg_rr_fast": (ctypes.c_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _i64, _vp]),
     "msgwam_rhs_rays": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp]),
@@ -89,6 +91,8 @@ SIGNATURES = {
     "msgwam_compact": (ctypes.c_int, [_i64, _vp, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _vp]),
     "msgwam_host_stage_doubles": (_i64, [_i64, _i32]),
     "msgwam_rk3_column_host": (ctypes.c_int, [_PP, _i64, ctypes.POINTER(_vp)] + [_vp] * 14 + [_vp]),
+    "msgwam_host_stage_doubles_nz": (_i64, [_i64, _i32]),
+    "msgwam_rk3_column_nz_host": (ctypes.c_int, [_PP, _i64, ctypes.POINTER(_vp)] + [_vp] * 17 + [_vp]),
 }
 
 

@@ -111,8 +111,9 @@ class Engine:
             self._gmax_nz = int(lib.msgwam_column_nz_max_levels())
         return self._gmax_nz
 
-    def column_step_nz(self, p: Params, state, dkk, dll, uu, vv, grid_devs):
-        """The fused column step with an N(z) profile (grid_devs carries it as its fifth entry); one GPU.
+    def column_step_nz(self, p: Params, state, dkk, dll, uu, vv, grid_devs, exchange=None):
+        """The fused column step with an N(z) profile (grid_devs carries it as its fifth entry); with the rays
+        sharded over several GPUs `exchange` (distributed.PeerExchange) carries the sums of the deposit.
         Returns (rr, drr, mm, dmm, uu, vv) after the step."""
         dens, lam, phi, rr, drr, kk, ll, mm, dmm = state
         n = rr.numel()
@@ -127,16 +128,17 @@ class Engine:
         outs = [self.empty(n) for _ in range(4)]
         uu_out, vv_out = self.empty(p.G), self.empty(p.G)
         check(lib.msgwam_column_step_nz(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), *[self.ptr(t) for t in outs],
-                                        self.ptr(uu_out), self.ptr(vv_out), None, self.stream), "msgwam_column_step_nz")
+                                        self.ptr(uu_out), self.ptr(vv_out), exchange.next(2) if exchange is not None else None,
+                                        self.stream), "msgwam_column_step_nz")
         self.launches += 2
         return outs[0], outs[1], outs[2], outs[3], uu_out, vv_out
 
-    def host_stage(self, n: int, G: int):
-        key = (n, G)
+    def host_stage(self, n: int, G: int, nz: bool = False):
+        key = (n, G, bool(nz))
         s = self._stage.get(key)
         if s is None:
             self._stage.clear()                 # one staging buffer at a time
-            s = self.empty(int(lib.msgwam_host_stage_doubles(n, G)))
+            s = self.empty(int((lib.msgwam_host_stage_doubles_nz if nz else lib.msgwam_host_stage_doubles)(n, G)))
             self._stage[key] = s
         return s
 
@@ -161,7 +163,9 @@ class Engine:
                     self.ptr(devs[4]) if len(devs) > 4 else _vp(0))
 
     def derived_statics(self, phi, dkk, dll, two_rot):
-        """ff = 2*ROT*sin(phi), pkl = dkk*dll on the device; cached on (storage, version) of the inputs."""
+        """ff = 2*ROT*sin(phi), pkl = dkk*dll on the device; cached on (storage, version) of the inputs.  The cache
+        entry keeps the three keyed tensors alive, so the caching allocator cannot hand their addresses to
+        different data while the key is still in use (a freed-and-reused address would match with stale values)."""
         key = tuple((t.data_ptr(), t._version, t.numel()) for t in (phi, dkk, dll)) + (two_rot,)
         if self._derived is not None and self._derived[0] == key:
             return self._derived[1], self._derived[2]
@@ -170,7 +174,7 @@ class Engine:
         check(lib.msgwam_derive_statics(self.ptr(phi), self.ptr(dkk), self.ptr(dll), self.ptr(ff), self.ptr(pkl),
                                         n, two_rot, self.stream), "msgwam_derive_statics")
         self.launches += 1
-        self._derived = (key, ff, pkl)
+        self._derived = (key, ff, pkl, (phi, dkk, dll))
         return ff, pkl
 
     # ---- fused column step on device tensors ---------------------------------------------------

@@ -33,12 +33,22 @@ class PeerExchange:
         if os.environ.get("MSGWAM_NCCL_ALLREDUCE", "0") == "1" or dist.get_world_size() > _cabi.MAX_PEERS:
             return None
         if G not in cls._cache:
+            ex, why = None, ""
             try:
-                cls._cache[G] = cls(G)
+                ex = cls(G)
             except Exception as exc:                      # no P2P / symmetric memory on this system
-                import warnings
-                warnings.warn("msgwam_b200: peer-memory all-reduce unavailable (%s); using NCCL" % (exc,))
-                cls._cache[G] = None
+                why = str(exc)
+            # the choice between peer memory and NCCL must be the same on every rank: one rank polling inboxes while
+            # another waits in an NCCL all-reduce would hang both
+            import torch
+            ok = torch.tensor([1 if ex is not None else 0], dtype=torch.int32, device=Engine.get().device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if ex is not None or why:
+                    import warnings
+                    warnings.warn("msgwam_b200: peer-memory all-reduce unavailable on some rank (%s); all ranks use NCCL" % (why or "another rank",))
+                ex = None
+            cls._cache[G] = ex
         return cls._cache[G]
 
     def __init__(self, G):
@@ -55,6 +65,9 @@ class PeerExchange:
         self.handle.barrier()                             # every inbox is zeroed before anyone pushes
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.epoch = 0
+        import os
+        if os.environ.get("MSGWAM_PEER_TIMEOUT_S"):
+            _cabi.check(_cabi.lib.msgwam_set_peer_timeout(float(os.environ["MSGWAM_PEER_TIMEOUT_S"])), "msgwam_set_peer_timeout")
 
     def next(self, count=1):
         """msgwam_peers_t for the next `count` reductions (the struct carries the epoch of the first)."""
@@ -64,6 +77,11 @@ class PeerExchange:
         for r, ptr in enumerate(self.ptrs):
             pe.inbox[r] = ptr
         return pe
+
+
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
 
 def all_reduce_sum(t):
@@ -88,6 +106,10 @@ def rk3_host_sharded(lprop, dt, var):
     p = lprop._params(dt)
     if p.hprop or p.saturate_online:
         raise NotImplementedError("sharded host path covers the column mode (HPROP off, saturate_online off)")
+    prof = lprop._bvf_profile()                 # N(z) extension: rr, drr, mm, dmm change; needs the peer exchange
+    exchange = PeerExchange.get(p.G)
+    if prof is not None and exchange is None and _world() > 1:
+        raise NotImplementedError("the sharded host path with an N(z) profile needs the peer-memory exchange")
     n = int(np.size(var[3]))
     host = [lprop._host_f64(a, n) for a in var[:9]]
     dkk, dll = lprop._host_f64(lprop.statics['dkk'], n), lprop._host_f64(lprop.statics['dll'], n)
@@ -106,22 +128,31 @@ def rk3_host_sharded(lprop, dt, var):
     # dens, phi, rr, drr, kk, ll, mm, dmm (lam is not needed on the device)
     dev = {i: up(k, host[i]) for k, i in enumerate((0, 2, 3, 4, 5, 6, 7, 8))}
     skey = (id(lprop.statics['dkk']), id(lprop.statics['dll']), dkk.ctypes.data, dll.ctypes.data)
-    if st["statics"] != skey:
+    if not lprop._statics_frozen or st["statics"] != skey:       # see libprop.freeze_statics
         up(8, dkk); up(9, dll)
         st["statics"] = skey
     state = [dev[0], dev[2], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8]]
     uu = torch.from_numpy(np.ascontiguousarray(var[9], dtype=np.float64)).to(eng.device, non_blocking=True)
     vv = torch.from_numpy(np.ascontiguousarray(var[10], dtype=np.float64)).to(eng.device, non_blocking=True)
     gd = lprop._grid_devs(eng)
-    rr_new, mm_new, uu_new, vv_new = eng.column_step(p, state, slab[8, :n], slab[9, :n], uu, vv, gd, reduce_fn=all_reduce_sum,
-                                                     exchange=PeerExchange.get(p.G))
-    outs = [lprop._pinned_empty(eng, n), lprop._pinned_empty(eng, n), lprop._pinned_empty(eng, p.G), lprop._pinned_empty(eng, p.G)]
-    for o, t in zip(outs, (rr_new, mm_new, uu_new, vv_new)):
+    if prof is not None:
+        rr_new, drr_new, mm_new, dmm_new, uu_new, vv_new = eng.column_step_nz(p, state, slab[8, :n], slab[9, :n], uu, vv, gd,
+                                                                             exchange=exchange)
+        res = (rr_new, mm_new, uu_new, vv_new, drr_new, dmm_new)
+    else:
+        res = eng.column_step(p, state, slab[8, :n], slab[9, :n], uu, vv, gd, reduce_fn=all_reduce_sum, exchange=exchange)
+    outs = [lprop._pinned_empty(eng, t.numel()) for t in res]
+    for o, t in zip(outs, res):
         torch.from_numpy(o).copy_(t, non_blocking=True)
-    torch.cuda.current_stream(eng.device).synchronize()
+    err = eng.column_work(p.G)[int(_cabi.lib.msgwam_column_error_offset(p.G))]
+    err_host = err.to("cpu", non_blocking=False)          # synchronises the stream: the copies above have landed
+    if float(err_host) != 0.0:
+        err.zero_()
+        raise _cabi.MsgwamError("a bounded device-side wait timed out (code %g): a peer did not deliver its deposit, or the "
+                                "mean-flow slices did not arrive; the step's results are invalid" % float(err_host))
     u = lprop._unchanged
-    return lprop._pack11([u(host[0]), u(host[1]), u(host[2]), outs[0], u(host[4]), u(host[5]), u(host[6]), outs[1],
-                          u(host[8]), outs[2], outs[3]])
+    return lprop._pack11([u(host[0]), u(host[1]), u(host[2]), outs[0], outs[4] if prof is not None else u(host[4]), u(host[5]),
+                          u(host[6]), outs[1], outs[5] if prof is not None else u(host[8]), outs[2], outs[3]])
 
 
 def shard_range(n: int, rank: int, world: int):

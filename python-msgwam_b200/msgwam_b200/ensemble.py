@@ -34,8 +34,11 @@ def _dist():
 
 class RayEnsemble:
     def __init__(self, state, dkk, dll, rr_mm_area, uu, vv, grid, grids, rhobar, pressure_gradient, *,
-                 bvf, phi0, kappa=1.0, saturate_online=False, hprop=False, distributed=None):
-        """state: the 9 per-ray arrays of this rank's slice (numpy or torch); grid fields are replicated."""
+                 bvf, phi0, kappa=1.0, saturate_online=False, hprop=False, distributed=None,
+                 rot_earth=_cabi.ROT_EARTH_DEFAULT, rad_earth=_cabi.RAD_EARTH_DEFAULT):
+        """state: the 9 per-ray arrays of this rank's slice (numpy or torch); grid fields are replicated.
+        rot_earth / rad_earth: the module constants ROT_EARTH / RAD_EARTH of the reference (L:3-4), should the caller
+        have overridden them."""
         self.eng = Engine.get()
         eng = self.eng
         n = int(np.size(state[3])) if not hasattr(state[3], "numel") else int(state[3].numel())
@@ -52,7 +55,8 @@ class RayEnsemble:
         names = STATE + STATICS
         for i, (nm, a) in enumerate(zip(names, list(state) + [dkk, dll, rr_mm_area])):
             self._slab[i, :n].copy_(eng.dev(a, n))
-        self.cfg = dict(bvf=bvf, phi0=phi0, kappa=kappa, saturate_online=saturate_online, hprop=hprop)
+        self.cfg = dict(bvf=bvf, phi0=phi0, kappa=kappa, saturate_online=saturate_online, hprop=hprop,
+                        rot_earth=rot_earth, rad_earth=rad_earth)
         self.grid_host, self.grids_host = np.asarray(grid, dtype=np.float64), np.asarray(grids, dtype=np.float64)
         self.G = len(self.grids_host)
         self.grid_devs = tuple(eng.dev(a) for a in (self.grid_host, self.grids_host,
@@ -85,7 +89,7 @@ class RayEnsemble:
         eng = self.eng
         check(lib.msgwam_derive_statics(eng.ptr(self.field("phi")), eng.ptr(self.field("dkk")), eng.ptr(self.field("dll")),
                                         eng.ptr(self.field("ff")), eng.ptr(self.field("pkl")), self.n,
-                                        2 * _cabi.ROT_EARTH_DEFAULT, eng.stream), "msgwam_derive_statics")
+                                        2 * self.cfg["rot_earth"], eng.stream), "msgwam_derive_statics")
         eng.launches += 1
 
     def params(self, dt) -> _cabi.Params:
@@ -170,7 +174,8 @@ class RayEnsemble:
                     self._reduce(self.work[4 * nc:6 * nc])
                     check(lib.msgwam_column_finish(p, g, eng.ptr(self.uu), eng.ptr(self.vv), eng.ptr(self.work),
                                                    eng.ptr(self._uu2), eng.ptr(self._vv2), s), "msgwam_column_finish")
-                eng.launches += 3
+                    eng.launches += 1
+                eng.launches += 2
                 self.uu, self._uu2 = self._uu2, self.uu
                 self.vv, self._vv2 = self._vv2, self.vv
             else:
@@ -232,6 +237,8 @@ class RayEnsemble:
             self.steps_done += 1
             if history is not None and self.steps_done % history.every == 0:
                 history.record(self, self.steps_done)
+        if self.exchange is not None:
+            self.check_errors()                     # a missing peer must not yield silently invalid results
 
     # ---- deletion ---------------------------------------------------------------------------------
     def compact(self, dt=0.0, m_crit=float("inf")) -> int:
@@ -256,18 +263,29 @@ class RayEnsemble:
                                  eng.stream), "msgwam_compact")
         eng.launches += 4
         self._slab, self._slab2 = self._slab2, self._slab
-        self.n = int(count.item())
+        off = int(lib.msgwam_column_error_offset(self.G))
+        both = torch.stack((count[0].to(torch.float64), self.work[off])).cpu()     # one synchronising read for both
+        self.n = int(both[0].item())
+        self._raise_on(float(both[1].item()))
         return self.n
 
+    def _raise_on(self, word):
+        if word != 0.0:
+            self.work[int(lib.msgwam_column_error_offset(self.G))] = 0.0
+            what = {1.0: "a peer did not deliver its deposit (peer-memory all-reduce timed out)",
+                    2.0: "the mean-flow slices of pass B did not all arrive (its CTAs were not co-resident)"}.get(word, "code %g" % word)
+            raise _cabi.MsgwamError("a bounded device-side wait timed out: %s; the results since the last check are invalid" % what)
+
     def check_errors(self):
-        """Raise if a peer exchange timed out (synchronises the stream)."""
+        """Raise if a bounded device-side wait of a step since the last check timed out (synchronises the stream).
+        Called by every method that synchronises anyway: advance (sharded), compact, to_var, History.to_host."""
         off = int(lib.msgwam_column_error_offset(self.G))
-        if float(self.work[off].item()) != 0.0:
-            raise _cabi.MsgwamError("peer-memory all-reduce timed out: a rank did not deliver its deposit")
+        self._raise_on(float(self.work[off].item()))
 
     # ---- export -----------------------------------------------------------------------------------
     def to_var(self):
         """The reference's 11-slot state vector (numpy copies)."""
+        self.check_errors()
         out = np.empty(11, dtype=object)
         for i, nm in enumerate(STATE):
             out[i] = self.field(nm).cpu().numpy()
@@ -288,6 +306,7 @@ class History:
         eng = ens.eng
         self.buf = {f: eng.empty(nsnap, ens.G if f in ("uu", "vv") else ens.n) for f in self.fields}
         self.nsnap = nsnap
+        self.ens = ens
 
     def record(self, ens: RayEnsemble, step: int) -> None:
         if self.count >= self.nsnap:
@@ -299,6 +318,7 @@ class History:
         self.count += 1
 
     def to_host(self):
+        self.ens.check_errors()
         out = {f: self.buf[f][:self.count].cpu().numpy() for f in self.fields}
         out["steps"] = np.asarray(self.steps)
         return out

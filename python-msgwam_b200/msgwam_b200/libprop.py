@@ -44,9 +44,20 @@ _vp = ctypes.c_void_p
 # ------------------------------------------------------------------------------------------------
 def set_statics(**kwargs):
     """Store per-run constants (ray-volume widths dkk, dll and the r-m area) by name.  L:14-27"""
-    global _statics_on_device
+    global _statics_on_device, _statics_frozen
     statics.update(kwargs)
     _statics_on_device = None           # device copies of dkk, dll are refreshed at the next RK3
+    _statics_frozen = False
+
+
+def freeze_statics(frozen=True):
+    """Extension (not in the reference): promise that statics['dkk'] and statics['dll'] keep their values until the
+    next set_statics() call.  The reference reads the dict at every rhs evaluation (L:630-632), so by default the
+    host-buffer RK3 uploads both arrays with every call; after freeze_statics() their device copies are reused as
+    long as the very same array objects stay in the dict (16 bytes per ray less over PCIe per step)."""
+    global _statics_on_device, _statics_frozen
+    _statics_frozen = bool(frozen)
+    _statics_on_device = None
 
 
 def set_model_setup(**kwargs):
@@ -414,10 +425,12 @@ def _unchanged(a):
 
 _COPY_UNCHANGED = bool(int(__import__("os").environ.get("MSGWAM_COPY_UNCHANGED", "0")))
 _statics_on_device = None          # (id/pointer key of dkk, dll, n, stage tensor id) of the last upload
+_statics_frozen = False            # freeze_statics(): the caller promises not to edit dkk, dll in place
 
 
-def _rk3_numpy_column(eng, p, var):
-    """Host-buffer path: one C-ABI call copies the step's inputs in, steps, copies rr, mm, uu, vv out."""
+def _rk3_numpy_column(eng, p, var, prof=None):
+    """Host-buffer path: one C-ABI call copies the step's inputs in, steps, copies rr, mm, uu, vv out
+    (prof: the N(z) extension's profile on grids; then drr, dmm change as well and come back too)."""
     global _statics_on_device
     n = _size(var[3])
     G = p.G
@@ -436,13 +449,25 @@ def _rk3_numpy_column(eng, p, var):
     rr_new, mm_new = _pinned_empty(eng, n), _pinned_empty(eng, n)
     uu_new, vv_new = np.empty(G), np.empty(G)
     hp = (_vp * 9)(*[a.ctypes.data for a in host])
-    stage = eng.host_stage(n, G)
+    stage = eng.host_stage(n, G, prof is not None)
     work = eng.column_work(G)
     cp = lambda a: _vp(a.ctypes.data)
-    # per-run statics (L:722-726) stay on the device between calls while the caller keeps passing the very
-    # same arrays (same object, same buffer); set_statics() or a new array re-uploads them
+    # per-run statics (L:722-726): uploaded with every call (the reference reads the dict at every evaluation, and an
+    # in-place edit of statics['dkk'] must take effect) unless the caller froze them (freeze_statics) and keeps
+    # passing the very same arrays (same object, same buffer); set_statics() or a new array re-uploads them
     key = (id(statics['dkk']), id(statics['dll']), dkk.ctypes.data, dll.ctypes.data, n, stage.data_ptr())
-    reuse = _statics_on_device == key and not _COPY_UNCHANGED
+    reuse = _statics_frozen and _statics_on_device == key and not _COPY_UNCHANGED
+    if prof is not None:
+        bv = np.ascontiguousarray(prof, dtype=np.float64).reshape(G)
+        drr_new, dmm_new = _pinned_empty(eng, n), _pinned_empty(eng, n)
+        check(lib.msgwam_rk3_column_nz_host(p, n, hp, _vp(0) if reuse else cp(dkk), _vp(0) if reuse else cp(dll), cp(uu), cp(vv),
+                                            cp(g), cp(gs), cp(rho), cp(pg), cp(bv),
+                                            cp(rr_new), cp(drr_new), cp(mm_new), cp(dmm_new), cp(uu_new), cp(vv_new),
+                                            eng.ptr(stage), eng.ptr(work), eng.stream), "msgwam_rk3_column_nz_host")
+        _statics_on_device = key
+        eng.launches += 3
+        return _pack11([_unchanged(host[0]), _unchanged(host[1]), _unchanged(host[2]), rr_new, drr_new,
+                        _unchanged(host[5]), _unchanged(host[6]), mm_new, dmm_new, uu_new, vv_new])
     check(lib.msgwam_rk3_column_host(p, n, hp, _vp(0) if reuse else cp(dkk), _vp(0) if reuse else cp(dll), cp(uu), cp(vv),
                                      cp(g), cp(gs), cp(rho), cp(pg),
                                      cp(rr_new), cp(mm_new), cp(uu_new), cp(vv_new), eng.ptr(stage), eng.ptr(work),
@@ -480,6 +505,8 @@ def RK3(dt, var):
     column_nz = not p.hprop and not p.saturate_online and prof is not None and p.G <= eng.column_nz_max_levels()
     if column and not like_dev:
         return _rk3_numpy_column(eng, p, var)
+    if column_nz and not like_dev:
+        return _rk3_numpy_column(eng, p, var, prof)
     n = _size(var[3])
     state = [eng.dev(x, n) for x in var[:9]]
     uu, vv = eng.dev(var[9], p.G), eng.dev(var[10], p.G)

@@ -180,20 +180,54 @@ def column_ensemble(n: int, seed: int = 1234, ngrid: int = 1001, sheared: bool =
     return Scenario(name, 120., state, uu, vv, stat[0], stat[1], stat[2], grid, grids, rhobar, pg, model, hprop=False)
 
 
-def critical_level_ensemble(n: int, seed: int = 4321, ngrid: int = 1001) -> Scenario:
+def n_profile(grids):
+    """N(z) of BASELINE configs[2-3]: N^2 = 1e-4 (1 + 3 * (1 + tanh((z - 15 km) / 3 km)) / 2),
+    troposphere -> stratosphere, as the array of N on `grids` that the extension takes in model_config['bvf']."""
+    return np.sqrt(1e-4 * (1 + 3 * .5 * (1 + np.tanh((np.asarray(grids) - 15e3) / 3e3))))
+
+
+def nz_sheared_ensemble(n: int, seed: int = 1234, ngrid: int = 1001, amplitude: float = 0.01, shuffled: bool = False) -> Scenario:
+    """BASELINE.json configs[2] (and, sharded over 8 GPUs, configs[3]): the rays of column_ensemble in a sheared wind
+    (tanh jet of 40 m/s centred at 30 km plus a 5 m/s sine of 10 km wavelength) under the N^2(z) profile above, with
+    wave-action amplitudes that make the deposited flux feed back on the wind (raytracer.py:115-117 scaling)."""
+    sc = column_ensemble(n, seed=seed, ngrid=ngrid, sheared=True, amplitude=amplitude, shuffled=shuffled)
+    sc.model = dict(sc.model, bvf=n_profile(sc.grids))
+    sc.name = "nz_sheared_n%d" % n
+    return sc
+
+
+M_CRIT_STRESS = 2 * np.pi / 150.0     # |m| cut-off of the configs[4] stress scenario: vertical wavelength 150 m
+
+
+def critical_level_ensemble(n: int, seed: int = 4321, ngrid: int = 1001, stress: bool = False) -> Scenario:
     """BASELINE.json configs[4] (constant-N variant): a jet U(z) = 20 m/s * exp(-(z - 30 km)^2 / (2 (5 km)^2)).
     Rays whose horizontal wavenumber is parallel to the jet are refracted towards a critical level
     (|m| grows without bound, c_g -> 0: they pile up below the jet); antiparallel rays run out of the top.
-    Half of the rays have either sign of k; l = 0.  Ray deletion (RayEnsemble.compact) removes both kinds."""
+    Half of the rays have either sign of k; l = 0.  Ray deletion (RayEnsemble.compact) removes both kinds.
+
+    stress=True: the variant in which deletion HAPPENS within tens of steps -- a sharper, stronger jet (40 m/s,
+    sigma 2 km), rays launched on its lower flank (24-29 km) and, for the exit through the top, a tenth of them at
+    98-99.7 km; vertical wavelengths of 180-1000 m and horizontal ones of 5-30 km; use with M_CRIT_STRESS."""
     rng = np.random.default_rng(seed)
     NN = 0.01
     grid = np.linspace(0, 100e3, ngrid)
     grids = .5 * (grid[:-1] + grid[1:])
-    edges = np.linspace(0, 25e3, n + 1)
-    rr = .5 * (edges[:-1] + edges[1:])
-    drr = rng.uniform(50., 300., n)
-    mm = -2 * np.pi / rng.uniform(1e3, 5e3, n)
-    kk = 2 * np.pi / rng.uniform(20e3, 100e3, n) * rng.choice([-1., 1.], n)
+    if stress:
+        n_top = n // 10
+        lo = np.linspace(24e3, 29e3, n - n_top + 1)
+        hi = np.linspace(98e3, 99.7e3, n_top + 1)
+        rr = np.concatenate((.5 * (lo[:-1] + lo[1:]), .5 * (hi[:-1] + hi[1:])))
+        drr = rng.uniform(50., 300., n)
+        mm = -2 * np.pi / rng.uniform(180., 1e3, n)
+        kk = 2 * np.pi / rng.uniform(5e3, 30e3, n) * rng.choice([-1., 1.], n)
+        jet = (40., 30e3, 2e3)
+    else:
+        edges = np.linspace(0, 25e3, n + 1)
+        rr = .5 * (edges[:-1] + edges[1:])
+        drr = rng.uniform(50., 300., n)
+        mm = -2 * np.pi / rng.uniform(1e3, 5e3, n)
+        kk = 2 * np.pi / rng.uniform(20e3, 100e3, n) * rng.choice([-1., 1.], n)
+        jet = (20., 30e3, 5e3)
     ll = np.zeros(n)
     dmm = 1e-4 * np.abs(mm)
     dkk = np.full(n, 1e-4)
@@ -201,12 +235,12 @@ def critical_level_ensemble(n: int, seed: int = 4321, ngrid: int = 1001) -> Scen
     area = dmm * drr
     model = dict(bvf=NN, phi0=0.0, kappa=1., saturate_online=False)
     rhobar = _hydrostatic_rhobar(grids)
-    uu = 20. * np.exp(-(grids - 30e3) ** 2 / 2 / 5e3 ** 2)
+    uu = jet[0] * np.exp(-(grids - jet[1]) ** 2 / 2 / jet[2] ** 2)
     vv = np.zeros(grids.shape)
     omh = np.sqrt(NN ** 2 * (kk ** 2 + ll ** 2) / (kk ** 2 + ll ** 2 + mm ** 2))
     rho_ray = np.interp(rr, grids, rhobar)
-    per_cell = max(1.0, n * float(np.mean(drr)) / 25e3)
+    per_cell = max(1.0, n * float(np.mean(drr)) / (5e3 if stress else 25e3))
     dens = 0.1 ** 2 * rho_ray / 2 * omh / mm ** 2 / omh ** 2 * NN ** 2 / dkk / dll / dmm / per_cell
     pg = _geostrophic_pg(rhobar, 0.0, uu, vv)
-    return Scenario("critical_level_n%d" % n, 120., [dens, np.zeros(n), np.zeros(n), rr, drr, kk, ll, mm, dmm], uu, vv,
+    return Scenario("critical_level%s_n%d" % ("_stress" if stress else "", n), 120., [dens, np.zeros(n), np.zeros(n), rr, drr, kk, ll, mm, dmm], uu, vv,
                     dkk, dll, area, grid, grids, rhobar, pg, model, hprop=False)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MSGWAM_ABI_VERSION 4   /* 4: peer inboxes hold 16-byte self-validating cells; msgwam_saturation_step_commit */
+#define MSGWAM_ABI_VERSION 5   /* 5: msgwam_rays_t.bounds (fixed-point CTA histogram); N(z) host entry point; peer timeout */
 
 #define MSGWAM_E_BADARG      (-1)   /* null pointer / negative size / inconsistent arguments   */
 #define MSGWAM_E_GRID_SIZE   (-2)   /* G too small (< 3) or too large for the fused column kernels */
@@ -71,6 +71,14 @@ typedef struct msgwam_rays {
     double *stage1;      /* column mode only: 3*n doubles of scratch.  Pass A leaves the stage-1 increments and the
                             group velocity of state r1 there (dt*cg_rr(r0) | dt*dm_dt(r0) | cg_rr(r1)) so that
                             pass B starts at RK stage 2 instead of recomputing stage 1.                           */
+    double *bounds;      /* column mode only, may be NULL: 6 doubles of per-ensemble state that live next to a ray store
+                            which is advanced IN PLACE (zero them when the store is created or edited from outside).
+                            [0..2] = for the deposits D0, D1, D2 of the previous step, max over CTAs of the sum of
+                            |contribution| over the CTA's rays; [3..5] = the same, being gathered by the running step.
+                            With a known bound the CTA histogram that takes the deposits of lanes outside their warp's
+                            window accumulates in 64-bit fixed point with native integer atomics (deposit.cuh); NULL or
+                            zero: fp64 compare-and-swap atomics.  A bound that grows more than 8-fold within one step
+                            sets the error word (code 3).                                                          */
 } msgwam_rays_t;
 
 /* Background profiles on the 1-D mean-flow grid (L:6-9). */

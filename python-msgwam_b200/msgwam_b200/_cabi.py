@@ -30,7 +30,7 @@ class Params(ctypes.Structure):
     ]
 
 
-_RAY_FIELDS = ("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm", "dkk", "dll", "rr_mm_area", "ff", "pkl", "stage1")
+_RAY_FIELDS = ("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm", "dkk", "dll", "rr_mm_area", "ff", "pkl", "stage1", "bounds")
 
 
 class Rays(ctypes.Structure):
@@ -96,7 +96,7 @@ SIGNATURES = {
 }
 
 
-ABI_VERSION = 4          # MSGWAM_ABI_VERSION of include/msgwam_b200.h
+ABI_VERSION = 5          # MSGWAM_ABI_VERSION of include/msgwam_b200.h
 
 
 def _load():

@@ -25,6 +25,8 @@ from ._engine import Engine
 STATE = ("dens", "lam", "phi", "rr", "drr", "kk", "ll", "mm", "dmm")
 STATICS = ("dkk", "dll", "rr_mm_area")
 _vp = ctypes.c_void_p
+# MSGWAM_FIXED_HIST=0: the CTA histogram of the deposit always uses fp64 compare-and-swap atomics (developer switch)
+_FIXED_POINT_HISTOGRAM = __import__("os").environ.get("MSGWAM_FIXED_HIST", "1") != "0"
 
 
 def _dist():
@@ -52,6 +54,10 @@ class RayEnsemble:
         self._params_cache = None
         self._rays_cache = None
         self.steps_done = 0
+        # deposit bounds of the previous / running step (msgwam_rays_t.bounds): what lets the CTA histogram of the
+        # deposit accumulate in fixed point.  Zero = unknown (the next step takes the fp64 path and measures them).
+        self._bounds = eng.zeros(6)
+        self._slab_version = None
         names = STATE + STATICS
         for i, (nm, a) in enumerate(zip(names, list(state) + [dkk, dll, rr_mm_area])):
             self._slab[i, :n].copy_(eng.dev(a, n))
@@ -115,6 +121,7 @@ class RayEnsemble:
         if self._stage1 is None or self._stage1.numel() < hand * self.n:
             self._stage1 = self.eng.empty(max(hand * self.cap, 1))  # stage-1 hand-over between the two sweeps
         r.stage1 = self._stage1.data_ptr()
+        r.bounds = self._bounds.data_ptr() if _FIXED_POINT_HISTOGRAM else 0
         return r
 
     def _reduce(self, t):
@@ -134,6 +141,11 @@ class RayEnsemble:
         g = eng.grid_struct(self.grid_devs)
         column = self._is_column(p)
         assert _outs is None or (column and nsteps == 1)
+        if self._slab._version != self._slab_version:
+            # the store was written through torch (an upload, a caller editing a field() view): the deposit bounds of
+            # the last step no longer describe it
+            self._bounds.zero_()
+            self._slab_version = self._slab._version
         sharded = self.dist is not None and self.dist.get_world_size() > 1
         column_nz = (not p.hprop and not p.saturate_online and len(self.grid_devs) == 5 and
                      (not sharded or self.exchange is not None) and self.G <= eng.column_nz_max_levels())
@@ -263,6 +275,7 @@ class RayEnsemble:
                                  eng.stream), "msgwam_compact")
         eng.launches += 4
         self._slab, self._slab2 = self._slab2, self._slab
+        self._slab_version = None                   # the rays are dealt out to the CTAs anew: deposit bounds unknown
         off = int(lib.msgwam_column_error_offset(self.G))
         both = torch.stack((count[0].to(torch.float64), self.work[off])).cpu()     # one synchronising read for both
         self.n = int(both[0].item())
@@ -272,9 +285,12 @@ class RayEnsemble:
     def _raise_on(self, word):
         if word != 0.0:
             self.work[int(lib.msgwam_column_error_offset(self.G))] = 0.0
-            what = {1.0: "a peer did not deliver its deposit (peer-memory all-reduce timed out)",
-                    2.0: "the mean-flow slices of pass B did not all arrive (its CTAs were not co-resident)"}.get(word, "code %g" % word)
-            raise _cabi.MsgwamError("a bounded device-side wait timed out: %s; the results since the last check are invalid" % what)
+            self._bounds.zero_()
+            what = {1.0: "a peer did not deliver its deposit (the bounded wait of the peer-memory all-reduce timed out)",
+                    2.0: "the mean-flow slices of pass B did not all arrive in time (its CTAs were not co-resident)",
+                    3.0: "the deposited flux grew more than 8-fold within one step, beyond what the fixed-point histogram of "
+                         "the deposit was scaled for"}.get(word, "code %g" % word)
+            raise _cabi.MsgwamError("device-side check failed: %s; the results since the last check are invalid" % what)
 
     def check_errors(self):
         """Raise if a bounded device-side wait of a step since the last check timed out (synchronises the stream).

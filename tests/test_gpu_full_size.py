@@ -188,3 +188,41 @@ def test_compaction_reads_any_non_zero_flag_byte_as_keep():
     want = np.flatnonzero(flags != 0).astype(np.float64)
     assert int(count.item()) == len(want)
     assert np.array_equal(dst[:len(want)].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("profile", [False, True])
+def test_fixed_point_histogram_bounds_protocol(profile):
+    """The CTA histogram of the deposit accumulates in 64-bit fixed point once the previous step has measured a bound of
+    the deposited flux (msgwam_rays_t.bounds): the first step of an ensemble runs the fp64 path and leaves bounds > 0;
+    later steps stay within the grid tolerance on a shuffled (all lanes outliers) ensemble; an edit of the store
+    through torch resets the bounds; a flux that grows more than 8-fold behind the ensemble's back raises."""
+    from msgwam_b200 import _cabi
+    from msgwam_b200.ensemble import RayEnsemble
+    mk = scenarios.nz_sheared_ensemble if profile else (lambda n, **kw: scenarios.column_ensemble(n, ngrid=1001, sheared=True, **kw))
+    sc = mk(150_007, seed=21, amplitude=0.3, shuffled=True)
+    ens = RayEnsemble.from_scenario(sc)
+    assert float(ens._bounds.abs().sum()) == 0.0
+    ens.step(sc.dt)
+    b1 = ens._bounds.cpu().numpy().copy()
+    assert (b1[:3] > 0).all() and (b1[3:] == 0).all(), b1
+    ens.step(sc.dt, 3)                                          # fixed-point steps
+    orc = oracle.Oracle(sc.oracle_cfg(), nthreads=oracle.max_threads())
+    want = sc.var()
+    for _ in range(4):
+        want = orc.RK3(sc.dt, want)
+    assert_state_close(ens.to_var(), want, ray_tol=1e-12, grid_tol=1e-11, tag="fixed point", start=sc.var())
+    # an edit through torch invalidates the bounds: the next step measures them again and the result stays right
+    ens.field("dens").mul_(20.0)
+    ens.step(sc.dt)
+    b2 = ens._bounds.cpu().numpy()
+    assert np.all(b2[:3] > 10.0 * b1[:3]), (b1, b2)
+    ens.check_errors()
+    # the same growth behind the ensemble's back (version counter restored by hand): the step flags it
+    ens.field("dens").mul_(20.0)
+    ens._slab_version = ens._slab._version
+    ens.step(sc.dt)
+    with pytest.raises(_cabi.MsgwamError):
+        ens.check_errors()
+    ens.step(sc.dt, 2)                                          # bounds were reset: usable again
+    ens.check_errors()
+    assert np.isfinite(ens.to_var()[9]).all()

@@ -179,6 +179,13 @@ int msgwam_column_step_nz(const msgwam_params_t *p, const msgwam_rays_t *rays, i
 int32_t msgwam_column_nz_max_levels(void);
 /* offset (in doubles) inside d_work of the error word set by a timed-out peer exchange (0.0 = ok) */
 int64_t msgwam_column_error_offset(int32_t G);
+/* Deposit bounds of a ray store whose bounds are unknown (a new store, a store edited from outside): one cheap sweep
+ * sets rays->bounds[0..2] to the bound of wave_projection(var = 0) at the current state (L:137-149: max over CTAs of the
+ * sum of |dkk dll dmm| (|cg k dens| + |cg l dens|) over the CTA's rays) and [3..5] to zero.  The column step that
+ * follows then accumulates its deposits in fixed point (see msgwam_rays_t.bounds) and measures the bounds for the
+ * step after it.  grid->bvf != NULL: for msgwam_column_step_nz. */
+int msgwam_column_bounds(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                         const msgwam_grid_t *grid, void *stream);
 /* bound of the device-side polls of the peer exchange in seconds (default 120): a rank that is merely late must
  * never reach it; when it fires the error word is set and the host binding raises at its next synchronisation */
 int msgwam_set_peer_timeout(double seconds);

@@ -155,6 +155,53 @@ struct SplitTargets {
     }
 };
 
+// one ray volume's contributions to the fixed-point CTA histogram (sink.scale != 0)
+template <class Sink>
+__device__ __forceinline__ void deposit_fixed(int nlow, int nup, double rl, double ru, double psv, double v0, double v1,
+                                              double dz, double rdz, const double *__restrict__ g, const Sink &sink)
+{
+    // scaling by a power of two commutes with the rounding of t * v, so v is scaled once per ray.
+    // A cell weight is at most psv (1 + 2^-52): the ray fits if psv * |v| * scale stays far below 2^63.
+    const double w0 = mul(v0, sink.scale), w1 = mul(v1, sink.scale);
+    if (mul(psv, add(fabs(w0), fabs(w1))) < 2.0e18) {
+        sink.mark();
+        for (int c = nlow; c < nup; c += 2) {
+            const bool two = c + 1 < nup;
+            const int c1 = two ? c + 1 : c;
+            const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g), t1 = cell_weight(c1, rl, ru, psv, dz, rdz, g);
+            sink.add2_fixed(c, mul(t0, w0), mul(t0, w1), two, c1, mul(t1, w0), mul(t1, w1));
+        }
+    } else {                                            // non-finite or outsized: fp64 atomics on the global deposit
+        for (int c = nlow; c < nup; ++c) {
+            const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g);
+            atomicAdd(sink.g0 + c, mul(t0, v0)); atomicAdd(sink.g1 + c, mul(t0, v1));
+        }
+    }
+}
+
+// Window-free deposit of the fused column sweeps: every lane adds its ray volume's overlap weights (L:156-163) to the
+// CTA histogram -- in fixed point when the deposit bound is known (the normal case), else with fp64 compare-and-swap
+// atomics (correct for any input, slow when the lanes of a warp share cells).  The cost does not depend on how the rays
+// are ordered.
+template <class Sink>
+__device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, double rl, double ru, double psv, double v0,
+                                               double v1, double dz, double rdz, const double *__restrict__ g,
+                                               const Sink &sink)
+{
+    if (!ok) return;
+    if (sink.scale != 0.0) {                                    // CTA-uniform
+        deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, dz, rdz, g, sink);
+        return;
+    }
+    sink.mark();
+    for (int c = nlow; c < nup; c += 2) {
+        const bool two = c + 1 < nup;
+        const int c1 = two ? c + 1 : c;
+        const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g), t1 = cell_weight(c1, rl, ru, psv, dz, rdz, g);
+        sink.add2(c, mul(t0, v0), mul(t0, v1), two, c1, mul(t1, v0), mul(t1, v1));
+    }
+}
+
 template <int WIN, class Sink>
 __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double rl, double ru,
                                               double psv, double v0, double v1,
@@ -218,23 +265,7 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
     } else if (ok) {
         // outlier lane / unordered rays: add to the CTA histogram directly
         if (sink.scale != 0.0) {
-            // fixed point: scaling by a power of two commutes with the rounding of t * v, so v is scaled once per ray.
-            // A cell weight is at most psv (1 + 2^-52): the ray fits if psv * |v| * scale stays far below 2^63.
-            const double w0 = mul(v0, sink.scale), w1 = mul(v1, sink.scale);
-            if (mul(psv, add(fabs(w0), fabs(w1))) < 2.0e18) {
-                sink.mark();
-                for (int c = nlow; c < nup; c += 2) {
-                    const bool two = c + 1 < nup;
-                    const int c1 = two ? c + 1 : c;
-                    const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g), t1 = cell_weight(c1, rl, ru, psv, dz, rdz, g);
-                    sink.add2_fixed(c, mul(t0, w0), mul(t0, w1), two, c1, mul(t1, w0), mul(t1, w1));
-                }
-            } else {                                            // non-finite or outsized: fp64 atomics on the global deposit
-                for (int c = nlow; c < nup; ++c) {
-                    const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g);
-                    atomicAdd(sink.g0 + c, mul(t0, v0)); atomicAdd(sink.g1 + c, mul(t0, v1));
-                }
-            }
+            deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, dz, rdz, g, sink);
             return;
         }
         sink.mark();

@@ -53,14 +53,14 @@ static inline int64_t ray_slots(bool nz) { return nz ? 12 + 4 + 7 : 12 + 2 + 3; 
 int64_t msgwam_host_stage_doubles(int64_t n, int32_t G)
 {
     if (n < 0 || G < 3) return 0;
-    // then grid (G+1), grids, rhobar, pg (2G), uu, vv, uu_out, vv_out, (bvf: unused here, keeps one layout)
-    return ray_slots(false) * pad32(n) + pad32(G + 1) + 9 * pad32(G);
+    // then grid (G+1), grids, rhobar, pg (2G), uu, vv, uu_out, vv_out, (bvf: unused here, keeps one layout), deposit bounds
+    return ray_slots(false) * pad32(n) + pad32(G + 1) + 9 * pad32(G) + 32;
 }
 
 int64_t msgwam_host_stage_doubles_nz(int64_t n, int32_t G)
 {
     if (n < 0 || G < 3) return 0;
-    return ray_slots(true) * pad32(n) + pad32(G + 1) + 9 * pad32(G);
+    return ray_slots(true) * pad32(n) + pad32(G + 1) + 9 * pad32(G) + 32;
 }
 
 // h_bvf != NULL: the N(z) extension (msgwam_column_step_nz; rr, drr, mm, dmm come back), else the reference's scalar N
@@ -88,7 +88,7 @@ static int rk3_column_host_impl(const msgwam_params_t *p, int64_t n, const doubl
     double *d_st1 = d_out + (nz ? 4 : 2) * np;
     double *g = d + ray_slots(nz) * np;
     double *d_grid = g, *d_grids = g + pad32(G + 1), *d_rho = d_grids + gp, *d_pg = d_rho + gp, *d_uu = d_pg + 2 * gp,
-           *d_vv = d_uu + gp, *d_bvf = d_vv + gp, *d_uuo = d_bvf + gp, *d_vvo = d_uuo + gp;
+           *d_vv = d_uu + gp, *d_bvf = d_vv + gp, *d_uuo = d_bvf + gp, *d_vvo = d_uuo + gp, *d_bounds = d_vvo + gp;
     cudaError_t e;
 #define MW_H2D(dst, src, cnt)                                                                          \
     do {                                                                                               \
@@ -125,8 +125,11 @@ static int rk3_column_host_impl(const msgwam_params_t *p, int64_t n, const doubl
 #undef MW_H2D
     msgwam_rays_t r{};
     r.dens = d_dens; r.phi = d_phi; r.rr = d_rr; r.drr = d_drr; r.kk = d_kk; r.ll = d_ll; r.mm = d_mm; r.dmm = d_dmm;
-    r.dkk = d_dkk; r.dll = d_dll; r.ff = d_ff; r.pkl = d_pkl; r.stage1 = d_st1;
+    r.dkk = d_dkk; r.dll = d_dll; r.ff = d_ff; r.pkl = d_pkl; r.stage1 = d_st1; r.bounds = d_bounds;
     msgwam_grid_t gr{d_grid, d_grids, d_rho, d_pg, nz ? d_bvf : nullptr};
+    // a fresh state every call: one cheap sweep bounds its deposits so that the step's CTA histograms run in fixed point
+    rc = msgwam_column_bounds(p, &r, n, &gr, stream);
+    if (rc) return rc;
     if (nz) rc = msgwam_column_step_nz(p, &r, n, &gr, d_uu, d_vv, d_work, d_rro, d_drro, d_mmo, d_dmmo, d_uuo, d_vvo, nullptr, stream);
     else rc = msgwam_column_step(p, &r, n, &gr, d_uu, d_vv, d_work, d_rro, d_mmo, d_uuo, d_vvo, stream);
     if (rc) return rc;

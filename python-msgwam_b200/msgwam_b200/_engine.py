@@ -45,6 +45,7 @@ class Engine:
         self._scratch = None
         self._gmax = None
         self._gmax_nz = None
+        self._bounds = None        # deposit bounds of the stateless column calls (measured by a pre-pass every call)
         self.launches = 0          # kernels launched through this engine (bench.py reports it)
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -106,6 +107,15 @@ class Engine:
             t = self._scratch = self.empty(max(per_ray * n, 1))
         return t
 
+    def fresh_bounds(self, p, rays, n, g):
+        """Stateless column calls see a new state every time: msgwam_column_bounds measures the bound of its deposits, so
+        that the step's CTA histograms accumulate in fixed point (include/msgwam_b200.h: msgwam_rays_t.bounds)."""
+        if self._bounds is None:
+            self._bounds = self.zeros(8)
+        rays.bounds = self._bounds.data_ptr()
+        check(lib.msgwam_column_bounds(p, rays, n, g, self.stream), "msgwam_column_bounds")
+        self.launches += 1
+
     def column_nz_max_levels(self) -> int:
         if self._gmax_nz is None:
             self._gmax_nz = int(lib.msgwam_column_nz_max_levels())
@@ -124,6 +134,7 @@ class Engine:
             setattr(rays, k, t.data_ptr())
         rays.stage1 = self.ray_scratch(n, 7).data_ptr()
         g = self.grid_struct(grid_devs)
+        self.fresh_bounds(p, rays, n, g)
         work = self.column_work(p.G)
         outs = [self.empty(n) for _ in range(4)]
         uu_out, vv_out = self.empty(p.G), self.empty(p.G)
@@ -193,6 +204,7 @@ class Engine:
             setattr(rays, k, t.data_ptr())
         rays.stage1 = self.ray_scratch(n).data_ptr()
         g = self.grid_struct(grid_devs)
+        self.fresh_bounds(p, rays, n, g)
         work = self.column_work(p.G)
         rr_out = self.empty(n) if rr_out is None else rr_out
         mm_out = self.empty(n) if mm_out is None else mm_out

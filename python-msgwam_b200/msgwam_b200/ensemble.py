@@ -141,10 +141,12 @@ class RayEnsemble:
         g = eng.grid_struct(self.grid_devs)
         column = self._is_column(p)
         assert _outs is None or (column and nsteps == 1)
-        if self._slab._version != self._slab_version:
-            # the store was written through torch (an upload, a caller editing a field() view): the deposit bounds of
-            # the last step no longer describe it
-            self._bounds.zero_()
+        if self._slab._version != self._slab_version and _FIXED_POINT_HISTOGRAM and not p.hprop and not p.saturate_online:
+            # the store is new or was written through torch (an upload, a caller editing a field() view): the deposit
+            # bounds of the last step no longer describe it -- one cheap sweep measures them at the current state
+            check(lib.msgwam_column_bounds(p, self._build_rays(7 if len(self.grid_devs) == 5 else 3), self.n, g, eng.stream),
+                  "msgwam_column_bounds")
+            eng.launches += 1
             self._slab_version = self._slab._version
         sharded = self.dist is not None and self.dist.get_world_size() > 1
         column_nz = (not p.hprop and not p.saturate_online and len(self.grid_devs) == 5 and
@@ -286,6 +288,7 @@ class RayEnsemble:
         if word != 0.0:
             self.work[int(lib.msgwam_column_error_offset(self.G))] = 0.0
             self._bounds.zero_()
+            self._slab_version = None               # the next step measures the deposit bounds anew
             what = {1.0: "a peer did not deliver its deposit (the bounded wait of the peer-memory all-reduce timed out)",
                     2.0: "the mean-flow slices of pass B did not all arrive in time (its CTAs were not co-resident)",
                     3.0: "the deposited flux grew more than 8-fold within one step, beyond what the fixed-point histogram of "

@@ -74,7 +74,7 @@ for shuffled in (False, True):
 
 # ---- timing ----
 sc = make(n)
-for fixed in (False, True, False, True):
+for fixed, allh in ((False, 0), (True, 0), (False, 0), (True, 0)):
     ens_mod._FIXED_POINT_HISTOGRAM = fixed
     ens = RayEnsemble.from_scenario(sc)
     ens.step(sc.dt)
@@ -83,5 +83,5 @@ for fixed in (False, True, False, True):
     t = timed(ens, sc.dt, 10)
     ens.check_errors()
     print("%s %d rays, %-22s: ordered (steps 2-4) %.3f ms, dispersed (after %d steps) %.3f ms per step" % (
-        mode, n, "fixed-point histogram" if fixed else "fp64 CAS histogram", t_first, k_disp, t), flush=True)
+        mode, n, ("fixed-point, ALL lanes" if allh else "fixed-point histogram") if fixed else "fp64 CAS histogram", t_first, k_disp, t), flush=True)
     del ens

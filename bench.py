@@ -593,6 +593,7 @@ def extra_configs(args, eng, torch):
 
     def oop():
         check(lib.msgwam_column_step(p1, r1, n1, g1, P(e1.uu), P(e1.vv), P(e1.work), P(rr_o), P(mm_o), P(e1._uu2), P(e1._vv2), eng.stream), "column_step")
+    e1.measure_bounds(sc1.dt)
     timed(oop, 5)
     out["c1_ordered_out_of_place"] = entry(n1, timed(oop, k), note="round-1 headline regime: height-ordered ensemble, same input every step, L2 flushed")
     e1.step(sc1.dt, 30)
@@ -604,6 +605,7 @@ def extra_configs(args, eng, torch):
 
     def oop_s():
         check(lib.msgwam_column_step(ps, rs, n1, gs_, P(es.uu), P(es.vv), P(es.work), P(rr_o), P(mm_o), P(es._uu2), P(es._vv2), eng.stream), "column_step")
+    es.measure_bounds(scs.dt)
     timed(oop_s, 3)
     out["c1_shuffled_out_of_place"] = entry(n1, timed(oop_s, k), note="random ray order, L2 flushed")
     del e1, es

@@ -71,14 +71,15 @@ typedef struct msgwam_rays {
     double *stage1;      /* column mode only: 3*n doubles of scratch.  Pass A leaves the stage-1 increments and the
                             group velocity of state r1 there (dt*cg_rr(r0) | dt*dm_dt(r0) | cg_rr(r1)) so that
                             pass B starts at RK stage 2 instead of recomputing stage 1.                           */
-    double *bounds;      /* column mode only, may be NULL: 6 doubles of per-ensemble state that live next to a ray store
-                            which is advanced IN PLACE (zero them when the store is created or edited from outside).
-                            [0..2] = for the deposits D0, D1, D2 of the previous step, max over CTAs of the sum of
-                            |contribution| over the CTA's rays; [3..5] = the same, being gathered by the running step.
-                            With a known bound the CTA histogram that takes the deposits of lanes outside their warp's
-                            window accumulates in 64-bit fixed point with native integer atomics (deposit.cuh); NULL or
-                            zero: fp64 compare-and-swap atomics.  A bound that grows more than 8-fold within one step
-                            sets the error word (code 3).                                                          */
+    double *bounds;      /* column mode only, may be NULL: 16 doubles of per-ensemble state that live next to a ray store
+                            which is advanced IN PLACE.  [0..5] = for the deposits D0, D1, D2 of the previous step and
+                            each of their two flux components, the max over CTAs of the sum of |contribution| over the
+                            CTA's rays; [6..11] = the same, being gathered by the running step; [12] = 1.0 when [0..5] are
+                            valid (zero the 16 doubles when the store is created or edited from outside, or call
+                            msgwam_column_bounds).  With valid bounds the CTA histogram of the deposit accumulates in
+                            64-bit fixed point with native integer atomics (deposit.cuh); NULL or invalid: fp64
+                            compare-and-swap atomics.  A bound that grows more than 8-fold within one step sets the
+                            error word (code 3).                                                                    */
 } msgwam_rays_t;
 
 /* Background profiles on the 1-D mean-flow grid (L:6-9). */
@@ -180,8 +181,8 @@ int32_t msgwam_column_nz_max_levels(void);
 /* offset (in doubles) inside d_work of the error word set by a timed-out peer exchange (0.0 = ok) */
 int64_t msgwam_column_error_offset(int32_t G);
 /* Deposit bounds of a ray store whose bounds are unknown (a new store, a store edited from outside): one cheap sweep
- * sets rays->bounds[0..2] to the bound of wave_projection(var = 0) at the current state (L:137-149: max over CTAs of the
- * sum of |dkk dll dmm| (|cg k dens| + |cg l dens|) over the CTA's rays) and [3..5] to zero.  The column step that
+ * sets rays->bounds[0..5] to the bounds of wave_projection(var = 0) at the current state (L:137-149: max over CTAs of the
+ * sums of |dkk dll dmm cg k dens| and |dkk dll dmm cg l dens| over the CTA's rays), [6..11] to zero and [12] to 1.  The column step that
  * follows then accumulates its deposits in fixed point (see msgwam_rays_t.bounds) and measures the bounds for the
  * step after it.  grid->bvf != NULL: for msgwam_column_step_nz. */
 int msgwam_column_bounds(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,

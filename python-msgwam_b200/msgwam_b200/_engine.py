@@ -111,7 +111,7 @@ class Engine:
         """Stateless column calls see a new state every time: msgwam_column_bounds measures the bound of its deposits, so
         that the step's CTA histograms accumulate in fixed point (include/msgwam_b200.h: msgwam_rays_t.bounds)."""
         if self._bounds is None:
-            self._bounds = self.zeros(8)
+            self._bounds = self.zeros(16)
         rays.bounds = self._bounds.data_ptr()
         check(lib.msgwam_column_bounds(p, rays, n, g, self.stream), "msgwam_column_bounds")
         self.launches += 1

@@ -56,7 +56,7 @@ class RayEnsemble:
         self.steps_done = 0
         # deposit bounds of the previous / running step (msgwam_rays_t.bounds): what lets the CTA histogram of the
         # deposit accumulate in fixed point.  Zero = unknown (the next step takes the fp64 path and measures them).
-        self._bounds = eng.zeros(6)
+        self._bounds = eng.zeros(16)
         self._slab_version = None
         names = STATE + STATICS
         for i, (nm, a) in enumerate(zip(names, list(state) + [dkk, dll, rr_mm_area])):
@@ -144,10 +144,7 @@ class RayEnsemble:
         if self._slab._version != self._slab_version and _FIXED_POINT_HISTOGRAM and not p.hprop and not p.saturate_online:
             # the store is new or was written through torch (an upload, a caller editing a field() view): the deposit
             # bounds of the last step no longer describe it -- one cheap sweep measures them at the current state
-            check(lib.msgwam_column_bounds(p, self._build_rays(7 if len(self.grid_devs) == 5 else 3), self.n, g, eng.stream),
-                  "msgwam_column_bounds")
-            eng.launches += 1
-            self._slab_version = self._slab._version
+            self.measure_bounds(dt)
         sharded = self.dist is not None and self.dist.get_world_size() > 1
         column_nz = (not p.hprop and not p.saturate_online and len(self.grid_devs) == 5 and
                      (not sharded or self.exchange is not None) and self.G <= eng.column_nz_max_levels())
@@ -200,6 +197,16 @@ class RayEnsemble:
                 self.uu, self.vv = uu, vv
                 if p.hprop:
                     self._derive()                  # phi moved: ff = 2 Omega sin(phi) for the column kernels
+
+    def measure_bounds(self, dt):
+        """Deposit bounds of the store as it is (msgwam_column_bounds): what lets the next column step accumulate its
+        deposits in fixed point.  step() calls this whenever the store is new or was edited through torch."""
+        eng = self.eng
+        p = self.params(dt)
+        check(lib.msgwam_column_bounds(p, self._build_rays(7 if len(self.grid_devs) == 5 else 3), self.n,
+                                       eng.grid_struct(self.grid_devs), eng.stream), "msgwam_column_bounds")
+        eng.launches += 1
+        self._slab_version = self._slab._version
 
     # ---- the driver's loop on the device ------------------------------------------------------------
     def advance(self, dt, nsteps, saturate=True, history=None):

@@ -204,7 +204,7 @@ def test_fixed_point_histogram_bounds_protocol(profile):
     assert float(ens._bounds.abs().sum()) == 0.0
     ens.step(sc.dt)
     b1 = ens._bounds.cpu().numpy().copy()
-    assert (b1[:3] > 0).all() and (b1[3:] == 0).all(), b1
+    assert (b1[:6] > 0).all() and (b1[6:12] == 0).all() and b1[12] == 1.0, b1
     ens.step(sc.dt, 3)                                          # fixed-point steps
     orc = oracle.Oracle(sc.oracle_cfg(), nthreads=oracle.max_threads())
     want = sc.var()
@@ -215,7 +215,7 @@ def test_fixed_point_histogram_bounds_protocol(profile):
     ens.field("dens").mul_(20.0)
     ens.step(sc.dt)
     b2 = ens._bounds.cpu().numpy()
-    assert np.all(b2[:3] > 10.0 * b1[:3]), (b1, b2)
+    assert np.all(b2[:6] > 10.0 * b1[:6]), (b1, b2)
     ens.check_errors()
     # the same growth behind the ensemble's back (version counter restored by hand): the step flags it
     ens.field("dens").mul_(20.0)

@@ -60,7 +60,7 @@ for shuffled in (False, True):
         ens.step(scp.dt, 4)
         res[fixed] = ens.to_var()
         if fixed:
-            print("bounds after 4 steps:", ens._bounds.cpu().numpy()[:3])
+            print("bounds after 4 steps:", ens._bounds.cpu().numpy()[:6])
     want = scp.var()
     orc = oracle.Oracle(scp.oracle_cfg(), nthreads=oracle.max_threads())
     for _ in range(4):

@@ -180,6 +180,20 @@ int msgwam_column_step_nz(const msgwam_params_t *p, const msgwam_rays_t *rays, i
 int32_t msgwam_column_nz_max_levels(void);
 /* offset (in doubles) inside d_work of the error word set by a timed-out peer exchange (0.0 = ok) */
 int64_t msgwam_column_error_offset(int32_t G);
+/* The reference driver's loop body (R:175-188) as one call -- the RK3 step (msgwam_column_step / _p2p / _nz) with the
+ * post-step clamp  dens <- saturation(dt, dens, rr_old, (rr_new - rr_old) / 1, drr_old, (drr_new - drr_old) / dt, kk,
+ * ll, mm_old, (mm_new - mm_old) / dt, direct=True)  (L:561-610, bug for bug including R:184's `/ 1`) fused into the end
+ * of pass B, where both ends of the step are in registers.  d_dens_out may alias rays->dens (then only clamped rays
+ * are written); rays->rr_mm_area is read; peers: NULL on one GPU. */
+int msgwam_column_advance(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                          const msgwam_grid_t *grid, const double *d_uu, const double *d_vv, double *d_work,
+                          double *d_rr_out, double *d_mm_out, double *d_dens_out,
+                          double *d_uu_out, double *d_vv_out, const msgwam_peers_t *peers, void *stream);
+int msgwam_column_advance_nz(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                             const msgwam_grid_t *grid, const double *d_uu, const double *d_vv, double *d_work,
+                             double *d_rr_out, double *d_drr_out, double *d_mm_out, double *d_dmm_out,
+                             double *d_dens_out, double *d_uu_out, double *d_vv_out,
+                             const msgwam_peers_t *peers /* NULL: one GPU */, void *stream);
 /* Deposit bounds of a ray store whose bounds are unknown (a new store, a store edited from outside): one cheap sweep
  * sets rays->bounds[0..5] to the bounds of wave_projection(var = 0) at the current state (L:137-149: max over CTAs of the
  * sums of |dkk dll dmm cg k dens| and |dkk dll dmm cg l dens| over the CTA's rays), [6..11] to zero and [12] to 1.  The column step that

@@ -44,26 +44,6 @@ struct RhsArgs {
     double *tend[9];
 };
 
-// saturation() core (L:582-604): returns max_dens_final and whether the clamp triggers
-__device__ __forceinline__ bool saturation_limit(const msgwam_params_t &p, double dt, double dens, double rr,
-                                                 double rr_st, double drr, double drr_st, double kk, double ll,
-                                                 double mm, double mm_st, double dkk, double dll, double area,
-                                                 const double *__restrict__ grids, const double *__restrict__ rhobar,
-                                                 const double *__restrict__ bvf, double &maxd)
-{
-    const double rr_final = add(rr, mul(rr_st, dt));
-    const double drr_final = add(drr, mul(drr_st, dt));
-    const double mm_final = add(mm, mul(mm_st, dt));
-    const double dmm_final = dvd(area, drr_final);
-    const double rho = interp1(rr_final, grids, rhobar, p.G, p.inv_dz_grids);
-    const double kh2 = add(mul(kk, kk), mul(ll, ll));
-    const double omh = omega_from(kh2, mul(mm, mm), p.f0sq, n2_at(bvf, grids, p.G, p.inv_dz_grids, p.n2, rr));      // ext: N at rr_center
-    const double psv = mul(mul(dkk, dll), dmm_final);
-    const double n2f = n2_at(bvf, grids, p.G, p.inv_dz_grids, p.n2, rr_final);                                    // ext: N at rr_final
-    maxd = dvd(dvd(mul(mul(mul(p.k2half, rho), omh), n2f), mul(mm_final, mm_final)), sub(mul(omh, omh), p.f0sq));
-    return maxd < mul(dens, psv);
-}
-
 // rhs_default's nine ray tendencies (L:629-651), all branches, for ray i: x[9] receives the state, t[9] the tendencies
 // need_sat = false (the fused RK stage with saturate_online off) skips the saturation threshold, whose result the
 // reference multiplies by False (L:647): the tendency is then +0.0 instead of -0.0 where the threshold is exceeded,
@@ -131,7 +111,7 @@ __device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9]
     if (need_sat) {
         double maxd;
         const bool hit = saturation_limit(p, p.dt, dens, rr, drr_st, drr, ddrr_st, kk, ll, mm, dmm_st,
-                                          a.r.dkk[i], a.r.dll[i], a.r.rr_mm_area[i], a.grids, a.rhobar, a.bvf, maxd);
+                                          mul(a.r.dkk[i], a.r.dll[i]), a.r.rr_mm_area[i], a.grids, a.rhobar, a.bvf, maxd);
         st = hit ? dvd(sub(maxd, dens), p.dt) : 0.0;                          // L:612-615
     }
     x[0] = dens; x[1] = lam; x[2] = phi; x[3] = rr; x[4] = drr; x[5] = kk; x[6] = ll; x[7] = mm; x[8] = dmm;
@@ -441,7 +421,7 @@ __global__ void __launch_bounds__(NT) saturation_kernel(const SatArgs a)
         double maxd;
         const double dens = a.dens[i];
         const bool hit = saturation_limit(a.p, a.p.dt, dens, a.rr[i], a.rr_st[i], a.drr[i], a.drr_st[i], a.kk[i], a.ll[i],
-                                          a.mm[i], a.mm_st[i], a.dkk[i], a.dll[i], a.area[i], a.grids, a.rhobar, a.bvf, maxd);
+                                          a.mm[i], a.mm_st[i], mul(a.dkk[i], a.dll[i]), a.area[i], a.grids, a.rhobar, a.bvf, maxd);
         if (a.direct) a.out[i] = hit ? maxd : dens;                               // L:606-610
         else a.out[i] = hit ? dvd(sub(maxd, dens), a.p.dt) : 0.0;                 // L:612-615
     }
@@ -470,7 +450,7 @@ __global__ void __launch_bounds__(NT) saturation_step_kernel(const SatStepArgs a
         const double mm_st = dvd(sub(mm1, mm0), a.p.dt);                         // R:187
         double maxd;
         const bool hit = saturation_limit(a.p, a.p.dt, dens, rr0, rr_st, drr0, drr_st, a.kk[i], a.ll[i], mm0, mm_st,
-                                          a.dkk[i], a.dll[i], a.area[i], a.grids, a.rhobar, a.bvf, maxd);
+                                          mul(a.dkk[i], a.dll[i]), a.area[i], a.grids, a.rhobar, a.bvf, maxd);
         a.out[i] = hit ? maxd : dens;                                            // L:606-610
     }
 }

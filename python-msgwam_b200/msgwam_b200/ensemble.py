@@ -141,10 +141,7 @@ class RayEnsemble:
         g = eng.grid_struct(self.grid_devs)
         column = self._is_column(p)
         assert _outs is None or (column and nsteps == 1)
-        if self._slab._version != self._slab_version and _FIXED_POINT_HISTOGRAM and not p.hprop and not p.saturate_online:
-            # the store is new or was written through torch (an upload, a caller editing a field() view): the deposit
-            # bounds of the last step no longer describe it -- one cheap sweep measures them at the current state
-            self.measure_bounds(dt)
+        self._check_bounds(dt)
         sharded = self.dist is not None and self.dist.get_world_size() > 1
         column_nz = (not p.hprop and not p.saturate_online and len(self.grid_devs) == 5 and
                      (not sharded or self.exchange is not None) and self.G <= eng.column_nz_max_levels())
@@ -198,6 +195,13 @@ class RayEnsemble:
                 if p.hprop:
                     self._derive()                  # phi moved: ff = 2 Omega sin(phi) for the column kernels
 
+    def _check_bounds(self, dt):
+        p = self.params(dt)
+        if self._slab._version != self._slab_version and _FIXED_POINT_HISTOGRAM and not p.hprop and not p.saturate_online:
+            # the store is new or was written through torch (an upload, a caller editing a field() view): the deposit
+            # bounds of the last step no longer describe it -- one cheap sweep measures them at the current state
+            self.measure_bounds(dt)
+
     def measure_bounds(self, dt):
         """Deposit bounds of the store as it is (msgwam_column_bounds): what lets the next column step accumulate its
         deposits in fixed point.  step() calls this whenever the store is new or was edited through torch."""
@@ -212,48 +216,60 @@ class RayEnsemble:
     def advance(self, dt, nsteps, saturate=True, history=None):
         """The reference driver's time loop (raytracer.py:157-188) without leaving the device: nsteps times
         RK3, then -- unless online saturation is on (R:182) -- the post-step clamp saturation(direct=True)
-        on the propagated wave action (one kernel, msgwam_saturation_step).  `history` (a History) receives
-        strided snapshots in place of the driver's (nt_max + 1, n) host arrays (R:125-136, 178-180)."""
+        on the propagated wave action.  In the column modes the clamp is fused into the end of the step's second
+        sweep (msgwam_column_advance / _nz: two launches per step of the driver loop); the general modes run it as one
+        kernel after the step (msgwam_saturation_step).  `history` (a History) receives strided snapshots in place of
+        the driver's (nt_max + 1, n) host arrays (R:125-136, 178-180)."""
         eng = self.eng
         p = self.params(dt)
         clamp = saturate and not p.saturate_online
         if history is not None and history.count == 0:
             history.record(self, 0)
-        fused_commit = clamp and self._is_column(p)
-        for k in range(1, nsteps + 1):
-            if clamp:
-                if self._old is None or self._old.shape[1] < self.cap:
-                    self._old = eng.empty(3, self.cap)
-                old = self._old[:, :self.n]
-            if fused_commit:
-                # constant-N column step: only rr and mm change.  The step writes them out of place, and the clamp kernel
-                # -- which needs both ends of the step -- copies them into the ray store: no copies of the old state
-                self.step(dt, 1, _outs=(old[0], old[2]))
-                dens, gd = self.field("dens"), self.grid_devs
-                rr, drr, mm = self.field("rr"), self.field("drr"), self.field("mm")
-                check(lib.msgwam_saturation_step_commit(
-                    p, self.n, eng.ptr(dens), eng.ptr(rr), eng.ptr(old[0]), eng.ptr(drr), eng.ptr(drr),
-                    eng.ptr(self.field("kk")), eng.ptr(self.field("ll")), eng.ptr(mm), eng.ptr(old[2]),
-                    eng.ptr(self.field("dkk")), eng.ptr(self.field("dll")), eng.ptr(self.field("rr_mm_area")),
-                    eng.ptr(gd[1]), eng.ptr(gd[2]), _vp(0), eng.ptr(dens), eng.ptr(rr), eng.ptr(mm), eng.stream),
-                    "msgwam_saturation_step_commit")
-                eng.launches += 1
+        if not clamp:
+            for k in range(nsteps):
+                self.step(dt)
                 self.steps_done += 1
                 if history is not None and self.steps_done % history.every == 0:
                     history.record(self, self.steps_done)
-                continue
-            if clamp:
+            if self.exchange is not None:
+                self.check_errors()
+            return
+        sharded = self.dist is not None and self.dist.get_world_size() > 1
+        profile = len(self.grid_devs) == 5
+        fused = (not p.hprop and (not sharded or self.exchange is not None) and
+                 self.G <= (eng.column_nz_max_levels() if profile else eng.column_max_levels()))
+        P = eng.ptr
+        for k in range(1, nsteps + 1):
+            if fused:
+                self._check_bounds(dt)
+                g = eng.grid_struct(self.grid_devs)
+                rays = self._rays(hand=7 if profile else 3)
+                peers = self.exchange.next(2) if self.exchange is not None else None
+                rr, mm, dens = self.field("rr"), self.field("mm"), self.field("dens")
+                if profile:
+                    check(lib.msgwam_column_advance_nz(p, rays, self.n, g, P(self.uu), P(self.vv), P(self.work), P(rr),
+                                                       P(self.field("drr")), P(mm), P(self.field("dmm")), P(dens), P(self._uu2),
+                                                       P(self._vv2), peers, eng.stream), "msgwam_column_advance_nz")
+                else:
+                    check(lib.msgwam_column_advance(p, rays, self.n, g, P(self.uu), P(self.vv), P(self.work), P(rr), P(mm), P(dens),
+                                                    P(self._uu2), P(self._vv2), peers, eng.stream), "msgwam_column_advance")
+                eng.launches += 2
+                self.uu, self._uu2 = self._uu2, self.uu
+                self.vv, self._vv2 = self._vv2, self.vv
+            else:
+                if self._old is None or self._old.shape[1] < self.cap:
+                    self._old = eng.empty(3, self.cap)
+                old = self._old[:, :self.n]
                 old[0].copy_(self.field("rr")); old[1].copy_(self.field("drr")); old[2].copy_(self.field("mm"))
-            self.step(dt)
-            if clamp:
+                self.step(dt)
                 dens = self.field("dens")
                 gd = self.grid_devs
                 check(lib.msgwam_saturation_step(
-                    p, self.n, eng.ptr(dens), eng.ptr(old[0]), eng.ptr(self.field("rr")), eng.ptr(old[1]),
-                    eng.ptr(self.field("drr")), eng.ptr(self.field("kk")), eng.ptr(self.field("ll")), eng.ptr(old[2]),
-                    eng.ptr(self.field("mm")), eng.ptr(self.field("dkk")), eng.ptr(self.field("dll")),
-                    eng.ptr(self.field("rr_mm_area")), eng.ptr(gd[1]), eng.ptr(gd[2]),
-                    eng.ptr(gd[4]) if len(gd) > 4 else _vp(0), eng.ptr(dens), eng.stream), "msgwam_saturation_step")
+                    p, self.n, P(dens), P(old[0]), P(self.field("rr")), P(old[1]),
+                    P(self.field("drr")), P(self.field("kk")), P(self.field("ll")), P(old[2]),
+                    P(self.field("mm")), P(self.field("dkk")), P(self.field("dll")),
+                    P(self.field("rr_mm_area")), P(gd[1]), P(gd[2]),
+                    P(gd[4]) if len(gd) > 4 else _vp(0), P(dens), eng.stream), "msgwam_saturation_step")
                 eng.launches += 1
             self.steps_done += 1
             if history is not None and self.steps_done % history.every == 0:

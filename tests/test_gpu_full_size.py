@@ -226,3 +226,28 @@ def test_fixed_point_histogram_bounds_protocol(profile):
     ens.step(sc.dt, 2)                                          # bounds were reset: usable again
     ens.check_errors()
     assert np.isfinite(ens.to_var()[9]).all()
+
+
+@pytest.mark.parametrize("profile,amplitude", [(False, 1.0), (True, 1.0), (True, 0.05)])
+def test_fused_advance_matches_the_driver_loop_through_the_oracle(profile, amplitude):
+    """RayEnsemble.advance in the column modes = msgwam_column_advance / _nz: the RK3 step with the driver's post-step
+    clamp saturation(direct=True) (R:182-188, `/ 1` included) fused into the second sweep.  Oracle: the same loop
+    through RK3 and saturation of the CPU restatement; with amplitude 1 a good part of the rays is clamped."""
+    from msgwam_b200.ensemble import RayEnsemble
+    mk = scenarios.nz_sheared_ensemble if profile else (lambda n, **kw: scenarios.column_ensemble(n, ngrid=1001, sheared=True, **kw))
+    sc = mk(120_013, seed=33, amplitude=amplitude)
+    ens = RayEnsemble.from_scenario(sc)
+    orc = oracle.Oracle(sc.oracle_cfg(), nthreads=oracle.max_threads())
+    var = sc.var()
+    clamped = 0
+    steps = 3
+    for _ in range(steps):
+        out = orc.RK3(sc.dt, var)
+        dens = orc.saturation(sc.dt, out[0], var[3], (out[3] - var[3]) / 1, var[4], (out[4] - var[4]) / sc.dt, out[5], out[6],
+                              var[7], (out[7] - var[7]) / sc.dt, direct=True)
+        clamped += int(np.count_nonzero(dens != out[0]))
+        out[0] = dens
+        var = out
+    assert (clamped > 1000) == (amplitude >= 1.0), clamped
+    ens.advance(sc.dt, steps, saturate=True)
+    assert_state_close(ens.to_var(), var, ray_tol=1e-10, grid_tol=1e-10, tag="advance", start=sc.var())

@@ -599,6 +599,7 @@ def extra_configs(args, eng, torch):
     e1.step(sc1.dt, 30)
     out["c1_dispersed_in_place"] = entry(n1, timed(lambda: e1.step(sc1.dt), k), note="after 30 in-place steps, L2 flushed")
     out["c1_advance"] = entry(n1, timed(lambda: e1.advance(sc1.dt, 1), k), note="driver loop on the device: RK3 + post-step saturation clamp (raytracer.py:175-188), dispersed, L2 flushed")
+    out["c1_frozen_background_M2"] = entry(n1, timed(lambda: e1.step_frozen(sc1.dt), k), note="EXTENSION, a different scheme (mean flow frozen over the step, one deposit per step; never answers for RK3): one sweep, one launch per step; dispersed, L2 flushed")
     scs = scenarios.column_ensemble(n1, seed=1234, ngrid=1001, shuffled=True)
     es = RayEnsemble.from_scenario(scs)
     ps, gs_, rs = es.params(scs.dt), eng.grid_struct(es.grid_devs), es._rays()
@@ -609,6 +610,18 @@ def extra_configs(args, eng, torch):
     timed(oop_s, 3)
     out["c1_shuffled_out_of_place"] = entry(n1, timed(oop_s, k), note="random ray order, L2 flushed")
     del e1, es
+    # ---- constant N at the size of configs[2] (1e7 rays): the coupled step and the frozen-background mode ----
+    n7 = 10_000_000
+    sc7 = scenarios.column_ensemble(n7, seed=1234, ngrid=1001, sheared=True, amplitude=0.01)
+    e7 = RayEnsemble.from_scenario(sc7)
+    del sc7.state
+    e7.step(120.0, 30)
+    out["constN_sheared_1e7_in_place"] = entry(n7, timed(lambda: e7.step(120.0), k, flush_l2=False), note="constant N, sheared wind, 1e7 rays, dispersed; A = 96 B/ray-step -> %.0f GB/s algorithmic" % 0.0)
+    t7 = out["constN_sheared_1e7_in_place"]["ms_per_step"] * 1e-3
+    out["constN_sheared_1e7_in_place"]["note"] = "constant N, sheared wind, 1e7 rays, dispersed; 96 B/ray-step algorithmic = %.0f GB/s" % (96.0 * n7 / t7 / 1e9)
+    tf = timed(lambda: e7.step_frozen(120.0), k, flush_l2=False)
+    out["constN_sheared_1e7_frozen_background_M2"] = entry(n7, tf, note="EXTENSION (see c1_frozen_background_M2); 96 B/ray-step algorithmic = %.0f GB/s, real traffic 88 B/ray" % (96.0 * n7 / tf / 1e9))
+    del e7
     # ---- general-mode regimes: HPROP on, online saturation on, 1e6 rays ----
     for key, kw in (("hprop", dict(hprop=True)), ("saturate_online", dict(saturate_online=True))):
         scg = scenarios.column_ensemble(n1, seed=1234, ngrid=1001, sheared=True, amplitude=0.3, phi0=np.deg2rad(-40.0))

@@ -180,6 +180,16 @@ int msgwam_column_step_nz(const msgwam_params_t *p, const msgwam_rays_t *rays, i
 int32_t msgwam_column_nz_max_levels(void);
 /* offset (in doubles) inside d_work of the error word set by a timed-out peer exchange (0.0 = ok) */
 int64_t msgwam_column_error_offset(int32_t G);
+/* FROZEN-BACKGROUND MODE "M2" -- an extension under its own name, NOT the reference's RK3 + rhs_default (whose mean
+ * flow is part of the RK state, L:629, 665-674): all three RK stages of a ray in registers with uu, vv frozen over the
+ * step; one deposit, of the state at the END of the step; uu += dt * du_dt(vv, dF/dz), vv += dt * dv_dt(uu, dF/dz) once
+ * per step (L:523-558, 653-663).  The ray half is exactly the reference's RK3 (L:680-700) with model_config['rhs'] (L:691)
+ * set to rhs_default with du_st = dv_st = 0.  One launch per step; constant N, HPROP off, saturate_online off.
+ * peers: NULL on one GPU, else one reduction (epoch peers->epoch) of the deposit in the tail of the sweep. */
+int msgwam_column_step_frozen(const msgwam_params_t *p, const msgwam_rays_t *rays, int64_t n,
+                              const msgwam_grid_t *grid, const double *d_uu, const double *d_vv, double *d_work,
+                              double *d_rr_out, double *d_mm_out, double *d_uu_out, double *d_vv_out,
+                              const msgwam_peers_t *peers, void *stream);
 /* The reference driver's loop body (R:175-188) as one call -- the RK3 step (msgwam_column_step / _p2p / _nz) with the
  * post-step clamp  dens <- saturation(dt, dens, rr_old, (rr_new - rr_old) / 1, drr_old, (drr_new - drr_old) / dt, kk,
  * ll, mm_old, (mm_new - mm_old) / dt, direct=True)  (L:561-610, bug for bug including R:184's `/ 1`) fused into the end

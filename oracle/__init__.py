@@ -220,5 +220,45 @@ class Oracle:
         return out
 
 
+    def RK3_frozen(self, dt, var):
+        """ORACLE OF AN EXTENSION (frozen-background mode "M2"; no such stepper in the reference): composed
+        only of restated reference functions, the way SURVEY.md 7.3-1 prescribes --
+          rays : the reference's RK3 (L:693-698) with model_config['rhs'] (L:691) = rhs_default whose du_st, dv_st are
+                 replaced by zeros, so that uu, vv stay frozen over the step;
+          flow : once per step  pm_flux[:, 1:-1] = wave_projection(new rays, var=0); edge copies; diff / dz (L:653-663);
+                 uu += dt * du_dt(vv, grad[0]); vv += dt * dv_dt(uu, grad[1])  (L:523-558).
+        Pinned against exactly that composition of the live Python reference (tests/test_oracle_vs_reference.py) and the
+        golden fixture it produced (tests/golden/frozen_col.npz)."""
+        def rhs(v):
+            t = self.rhs_default(dt, v)
+            t[9] = np.zeros(self.G); t[10] = np.zeros(self.G)
+            return t
+        var = np.array(list(var), dtype=object)
+        qq = dt * rhs(var)                                   # L:693-698, on the object array like the reference
+        var = var + qq / 3
+        qq = dt * rhs(var) - 5 / 9 * qq
+        var = var + 15 / 16 * qq
+        qq = dt * rhs(var) - 153 / 128 * qq
+        var = var + 8 / 15 * qq
+        dens, lam, phi, rr, drr, kk, ll, mm, dmm, uu, vv = var
+        n = np.size(rr)
+        dkk, dll, _ = self._statics(n)
+        pm_flux = np.zeros((2, self.G + 1))
+        pm_flux[:, 1:-1] = self.wave_projection(dens, lam, phi, rr - .5 * drr, rr + .5 * drr, kk, ll, mm - .5 * dmm, mm + .5 * dmm,
+                                                dkk, dll, dmm, self.grids)
+        pm_flux[:, 0] = pm_flux[:, 1]
+        pm_flux[:, -1] = pm_flux[:, -2]
+        dz = np.diff(self.grid[:2])[0]
+        grad = (pm_flux[:, 1:] - pm_flux[:, :-1]) / dz
+        ff = 2 * ROT_EARTH * np.sin(self.cfg["phi0"])
+        du = ff * vv - self.rhobar ** -1 * (self.pg[0] + grad[0])          # du_dt, L:537
+        dv = -ff * uu - self.rhobar ** -1 * (self.pg[1] + grad[1])         # dv_dt, L:556
+        out = np.empty(11, dtype=object)
+        for i in range(9):
+            out[i] = var[i]
+        out[9], out[10] = uu + dt * du, vv + dt * dv
+        return out
+
+
 def max_threads() -> int:
     return int(_load().orc_max_threads())

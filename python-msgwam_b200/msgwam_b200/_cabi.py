@@ -73,6 +73,7 @@ SIGNATURES = {
     "msgwam_column_error_offset": (_i64, [_i32]),
     "msgwam_set_peer_timeout": (ctypes.c_int, [_dbl]),
     "msgwam_column_bounds": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp]),
+    "msgwam_column_step_frozen": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 7 + [ctypes.POINTER(Peers), _vp]),
     "msgwam_column_advance": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 8 + [ctypes.POINTER(Peers), _vp]),
     "msgwam_column_advance_nz": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 10 + [ctypes.POINTER(Peers), _vp]),
     "msgwam_debug_mid_event": (ctypes.c_int, [_vp]),

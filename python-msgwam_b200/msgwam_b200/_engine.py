@@ -231,6 +231,27 @@ class Engine:
         self.launches += 3
         return rr_out, mm_out, uu_out, vv_out
 
+    def column_step_frozen(self, p: Params, state, dkk, dll, uu, vv, grid_devs):
+        """Frozen-background mode "M2" (extension; msgwam_column_step_frozen) on device tensors.
+        Returns (rr_new, mm_new, uu_new, vv_new)."""
+        dens, lam, phi, rr, drr, kk, ll, mm, dmm = state
+        n = rr.numel()
+        ff, pkl = self.derived_statics(phi, dkk, dll, p.two_rot)
+        rays = Rays()
+        for k, t in (("dens", dens), ("phi", phi), ("rr", rr), ("drr", drr), ("kk", kk), ("ll", ll), ("mm", mm),
+                     ("dmm", dmm), ("dkk", dkk), ("dll", dll), ("ff", ff), ("pkl", pkl)):
+            setattr(rays, k, t.data_ptr())
+        rays.stage1 = self.ray_scratch(n).data_ptr()
+        g = self.grid_struct(grid_devs)
+        self.fresh_bounds(p, rays, n, g)
+        work = self.column_work(p.G)
+        rr_out, mm_out, uu_out, vv_out = self.empty(n), self.empty(n), self.empty(p.G), self.empty(p.G)
+        check(lib.msgwam_column_step_frozen(p, rays, n, g, self.ptr(uu), self.ptr(vv), self.ptr(work), self.ptr(rr_out),
+                                            self.ptr(mm_out), self.ptr(uu_out), self.ptr(vv_out), None, self.stream),
+              "msgwam_column_step_frozen")
+        self.launches += 1
+        return rr_out, mm_out, uu_out, vv_out
+
     # ---- general right-hand side on device tensors ----------------------------------------------
     def rhs_general(self, p: Params, state, statics, uu, vv, grid_devs, reduce_fn=None):
         """All 11 tendencies (9 ray arrays + du, dv) and the deposit, every branch of rhs_default."""

@@ -195,6 +195,31 @@ class RayEnsemble:
                 if p.hprop:
                     self._derive()                  # phi moved: ff = 2 Omega sin(phi) for the column kernels
 
+    def step_frozen(self, dt, nsteps=1):
+        """EXTENSION, not the reference's scheme (never used by step / advance): the frozen-background mode "M2" --
+        every ray runs its three RK stages in registers against the mean flow of the start of the step, the rays'
+        flux is deposited ONCE (at the end of the step) and uu += dt * du_dt(...), vv += dt * dv_dt(...) once per step
+        (msgwam_column_step_frozen: one sweep and one launch per step).  Constant N, HPROP and online saturation off."""
+        eng = self.eng
+        p = self.params(dt)
+        if not self._is_column(p):
+            raise _cabi.MsgwamError("step_frozen covers the constant-N column mode (HPROP off, saturate_online off)")
+        sharded = self.dist is not None and self.dist.get_world_size() > 1
+        if sharded and self.exchange is None:
+            raise _cabi.MsgwamError("step_frozen on several GPUs needs the peer-memory exchange")
+        self._check_bounds(dt)
+        g = eng.grid_struct(self.grid_devs)
+        rays = self._rays()
+        P = eng.ptr
+        rr, mm = self.field("rr"), self.field("mm")
+        for _ in range(nsteps):
+            check(lib.msgwam_column_step_frozen(p, rays, self.n, g, P(self.uu), P(self.vv), P(self.work), P(rr), P(mm),
+                                                P(self._uu2), P(self._vv2), self.exchange.next(1) if sharded else None,
+                                                eng.stream), "msgwam_column_step_frozen")
+            eng.launches += 1
+            self.uu, self._uu2 = self._uu2, self.uu
+            self.vv, self._vv2 = self._vv2, self.vv
+
     def _check_bounds(self, dt):
         p = self.params(dt)
         if self._slab._version != self._slab_version and _FIXED_POINT_HISTOGRAM and not p.hprop and not p.saturate_online:

@@ -530,6 +530,37 @@ def RK3(dt, var):
     return _pack11([_out(eng, t, like_dev) for t in slots])
 
 
+def rhs_frozen(dt, var_in):
+    """EXTENSION (not in the reference): rhs_default with the mean-flow tendencies du_st, dv_st replaced by zeros --
+    plugged into model_config['rhs'] (L:691) it makes RK3 advance the rays against a mean flow frozen over the step."""
+    t = rhs_default(dt, var_in)
+    t[9] = t[9] * 0
+    t[10] = t[10] * 0
+    return t
+
+
+def RK3_frozen(dt, var):
+    """EXTENSION (not in the reference; never used by RK3): one step of the frozen-background mode "M2" -- the rays
+    advance through the reference's RK3 with rhs = rhs_frozen (all three stages in registers of one fused CUDA sweep),
+    their pseudo-momentum flux is deposited once, at the end of the step, and the mean flow takes one forward-Euler
+    step with it: uu + dt * du_dt(vv, dF/dz), vv + dt * dv_dt(uu, dF/dz).  Same 11-slot state vector in and out as RK3.
+    Constant N with HPROP_GLOBAL and saturate_online off."""
+    statics['dkk'], statics['dll']
+    eng = _engine()
+    p = _params(dt)
+    if p.hprop or p.saturate_online or _bvf_profile() is not None or p.G > eng.column_max_levels():
+        raise NotImplementedError("RK3_frozen covers the constant-N column mode (HPROP_GLOBAL False, saturate_online False)")
+    like_dev = _any_dev(eng, *var)
+    n = _size(var[3])
+    state = [eng.dev(x, n) for x in var[:9]]
+    uu, vv = eng.dev(var[9], p.G), eng.dev(var[10], p.G)
+    dkk, dll = eng.dev(statics['dkk'], n), eng.dev(statics['dll'], n)
+    rr_new, mm_new, uu_new, vv_new = eng.column_step_frozen(p, state, dkk, dll, uu, vv, _grid_devs(eng))
+    slots = [state[0].clone(), state[1].clone(), state[2].clone(), rr_new, state[4].clone(), state[5].clone(),
+             state[6].clone(), mm_new, state[8].clone(), uu_new, vv_new]
+    return _pack11([_out(eng, t, like_dev) for t in slots])
+
+
 # default setup, as installed at import time by the reference (L:704-726)
 set_model_setup(
     u0=80, phi0=np.deg2rad(-60), sig_phi=np.deg2rad(3), rr0=30000, rr1=40000, sig_rr=10000, drr=1,

@@ -251,3 +251,38 @@ def test_fused_advance_matches_the_driver_loop_through_the_oracle(profile, ampli
     assert (clamped > 1000) == (amplitude >= 1.0), clamped
     ens.advance(sc.dt, steps, saturate=True)
     assert_state_close(ens.to_var(), var, ray_tol=1e-10, grid_tol=1e-10, tag="advance", start=sc.var())
+
+
+def test_frozen_background_mode_vs_reference_fixture_and_oracle(lprop):
+    """Extension "M2" (msgwam_column_step_frozen: all three RK stages in registers, mean flow frozen over the step, one
+    deposit and one mean-flow update per step) against the fixture composed from the unmodified reference's functions
+    through model_config['rhs'] (tests/golden/make_golden_frozen.py), and in place at 3e5 rays against the oracle."""
+    from conftest import load_golden
+    from helpers import scenario_from_npz
+    from msgwam_b200.ensemble import RayEnsemble
+    d = load_golden("frozen_col.npz")
+    sc = scenario_from_npz(d)
+    sc.install(lprop)
+    var = sc.var()
+    for step in (1, 2, 3):
+        var = lprop.RK3_frozen(sc.dt, var)
+        assert_state_close(var, [d["step%d_%s" % (step, nm)] for nm in FIELDS], ray_tol=1e-12, grid_tol=1e-11,
+                           tag="frozen fixture step %d" % step, start=sc.var())
+    # the plug-in route: reference-style RK3 with model_config['rhs'] = rhs_frozen advances the rays identically
+    lprop.set_model_setup(rhs=lprop.rhs_frozen)
+    rays_only = lprop.RK3(sc.dt, sc.var())
+    for i in (3, 7):
+        assert np.max(np.abs(np.asarray(rays_only[i]) - d["step1_" + FIELDS[i]]) / np.abs(d["step1_" + FIELDS[i]])) <= 1e-12
+    assert np.array_equal(np.asarray(rays_only[9]), sc.uu)
+    big = scenarios.column_ensemble(300_007, seed=8, ngrid=1001, sheared=True, amplitude=0.3)
+    ens = RayEnsemble.from_scenario(big)
+    ens.step_frozen(big.dt, 3)
+    orc = oracle.Oracle(big.oracle_cfg(), nthreads=oracle.max_threads())
+    want = big.var()
+    for _ in range(3):
+        want = orc.RK3_frozen(big.dt, want)
+    assert_state_close(ens.to_var(), want, ray_tol=1e-12, grid_tol=1e-11, tag="frozen ensemble", start=big.var())
+    # and it is a different scheme: the coupled step gives a different wind
+    ens2 = RayEnsemble.from_scenario(big)
+    ens2.step(big.dt, 3)
+    assert field_rel(ens2.to_var()[9], want[9]) > 1e-8

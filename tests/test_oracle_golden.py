@@ -130,3 +130,16 @@ def test_driver_fixture_matches_the_known_answers_recorded_in_the_survey():
     assert np.allclose(d["mm"][kend][:3], [-0.00304211131909678, -0.00302430454016963, -0.00299897575710608], rtol=1e-14, atol=0)
     assert np.allclose(d["dens"][kend][:3], [8.0293785331725159e9, 1.2631985534866663e10, 1.9293364183825668e10], rtol=1e-13, atol=0)
     assert abs(float(d["wa_max"]) - 3.8994466052014998) <= 1e-12 and abs(float(d["flux_diag_absmax"]) - 1.8943901432301569) <= 1e-12
+
+
+def test_frozen_background_oracle_vs_reference_fixture():
+    """oracle.RK3_frozen against the fixture that tests/golden/make_golden_frozen.py composed from the unmodified
+    reference's functions (extension "M2": frozen mean flow over the step, one deposit per step)."""
+    d = load_golden("frozen_col.npz")
+    sc = scenario_from_npz(d)
+    orc = oracle.Oracle(sc.oracle_cfg())
+    var = sc.var()
+    for step in (1, 2, 3):
+        var = orc.RK3_frozen(sc.dt, var)
+        for i, nm in enumerate(FIELDS):
+            assert np.array_equal(np.asarray(var[i], dtype=np.float64), d["step%d_%s" % (step, nm)]), (step, nm)

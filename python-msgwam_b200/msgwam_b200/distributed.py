@@ -160,3 +160,53 @@ def shard_range(n: int, rank: int, world: int):
     base, rem = divmod(int(n), int(world))
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+# ---- load re-balancing after deletion (no counterpart in the reference) -------------------------
+def rebalance_plan(counts):
+    """Transfers that even out per-rank ray counts: a list of (src, dst, n) with every rank ending within one ray of
+    the mean.  Deterministic in `counts`, so every rank computes the same plan without communication.  Surplus ranks
+    give away rays from the END of their store, in rank order, to the deficit ranks in rank order."""
+    counts = [int(c) for c in counts]
+    world, total = len(counts), sum(counts)
+    base, rem = divmod(total, world)
+    target = [base + (1 if r < rem else 0) for r in range(world)]
+    surplus = [(r, counts[r] - target[r]) for r in range(world) if counts[r] > target[r]]
+    deficit = [(r, target[r] - counts[r]) for r in range(world) if counts[r] < target[r]]
+    plan, di = [], 0
+    for src, s in surplus:
+        while s > 0:
+            dst, d = deficit[di]
+            n = min(s, d)
+            plan.append((src, dst, n))
+            s -= n; d -= n
+            deficit[di] = (dst, d)
+            if d == 0:
+                di += 1
+    return plan, target
+
+
+def exchange_rows(rows, count, plan, rank, dist=None):
+    """Carry out `plan` on a (count, nfields) row-major tensor `rows` of this rank (CPU with gloo, CUDA with NCCL):
+    returns (kept_rows_view, received_rows) -- the rays this rank keeps (a prefix of `rows`) and the ones it receives."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    nf = rows.shape[1]
+    send = [(dst, n) for src, dst, n in plan if src == rank]
+    recv = [(src, n) for src, dst, n in plan if dst == rank]
+    give = sum(n for _, n in send)
+    keep = count - give
+    got = torch.empty((sum(n for _, n in recv), nf), dtype=rows.dtype, device=rows.device)
+    ops, off = [], keep
+    for dst, n in send:                                   # the tail of the store goes out, in plan order
+        ops.append(dist.P2POp(dist.isend, rows[off:off + n].contiguous(), dst))
+        off += n
+    off = 0
+    for src, n in recv:
+        ops.append(dist.P2POp(dist.irecv, got[off:off + n], src))
+        off += n
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return rows[:keep], got

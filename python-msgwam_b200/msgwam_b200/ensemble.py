@@ -332,6 +332,40 @@ class RayEnsemble:
         self._raise_on(float(both[1].item()))
         return self.n
 
+    def rebalance(self) -> int:
+        """Even out the ray counts of the ranks after deletion has skewed them (the reference has neither
+        deletion nor ranks): surplus ranks hand the rays at the end of their store to deficit ranks, all fields of a ray
+        together.  Rays are independent given the mean flow, so any assignment gives the same physics; the order of the
+        rays in a rank's store changes.  Collective over the process group; returns this rank's new count."""
+        if self.dist is None or self.dist.get_world_size() < 2:
+            return self.n
+        from .distributed import exchange_rows, rebalance_plan
+        eng, torch, dist = self.eng, self.eng.torch, self.dist
+        counts = torch.zeros(dist.get_world_size(), dtype=torch.int64, device=eng.device)
+        counts[dist.get_rank()] = self.n
+        dist.all_reduce(counts)
+        plan, target = rebalance_plan(counts.tolist())
+        if not plan:
+            return self.n
+        rank = dist.get_rank()
+        gives = sum(n for src, _, n in plan if src == rank)
+        rows = self._slab[:, self.n - gives:self.n].t().contiguous() if gives else self._slab[:, :0].t().contiguous()
+        # only the rays that leave are transposed into rows (exchange_rows sends the tail of what it is given)
+        _, got = exchange_rows(rows, gives, plan, rank, dist)
+        new_n = self.n - gives + got.shape[0]
+        assert new_n == target[rank], (new_n, target[rank])
+        if new_n > self.cap:
+            grown = eng.empty(self._slab.shape[0], new_n)
+            grown[:, :self.n - gives].copy_(self._slab[:, :self.n - gives])
+            self._slab, self._slab2, self.cap = grown, None, new_n
+            self._stage1 = self._old = None
+        if got.shape[0]:
+            self._slab[:, self.n - gives:new_n].copy_(got.t())
+        self.n = new_n
+        self._rays_cache = None
+        self._slab_version = None
+        return self.n
+
     def _raise_on(self, word):
         if word != 0.0:
             self.work[int(lib.msgwam_column_error_offset(self.G))] = 0.0

@@ -174,6 +174,57 @@ def test_two_rank_gloo_deposit_allreduce(tmp_path):
         assert p.returncode == 0, o
 
 
+def test_rebalance_plan_evens_out_any_counts():
+    from msgwam_b200.distributed import rebalance_plan
+    rng = np.random.default_rng(3)
+    for counts in ([10, 0], [0, 0, 0], [5, 5, 5], [1000, 3, 0, 17, 250, 1, 999, 12], list(rng.integers(0, 10**6, 8))):
+        plan, target = rebalance_plan(counts)
+        after = list(counts)
+        for src, dst, n in plan:
+            assert n > 0 and src != dst
+            after[src] -= n; after[dst] += n
+        assert after == target and sum(after) == sum(counts) and max(after) - min(after) <= 1
+        assert all(counts[src] > target[src] for src, _, _ in plan) and all(counts[dst] < target[dst] for _, dst, _ in plan)
+
+
+_REBALANCE_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "python-msgwam_b200"))
+from msgwam_b200.distributed import exchange_rows, rebalance_plan
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+counts = [1003, 10]                                 # deletion emptied rank 1
+rows = torch.arange(counts[rank] * 3, dtype=torch.float64).reshape(counts[rank], 3) + 1e6 * rank
+plan, target = rebalance_plan(counts)
+kept, got = exchange_rows(rows, counts[rank], plan, rank, dist)
+mine = torch.cat([kept, got])
+assert mine.shape[0] == target[rank], (mine.shape, target)
+allrows = [None, None]
+dist.all_gather_object(allrows, mine.numpy())
+u = np.concatenate(allrows)
+want = np.concatenate([np.arange(c * 3, dtype=np.float64).reshape(c, 3) + 1e6 * r for r, c in enumerate(counts)])
+assert u.shape == want.shape and np.array_equal(np.sort(u[:, 0]), np.sort(want[:, 0]))      # every ray exactly once
+assert np.array_equal(u[np.argsort(u[:, 0])], want[np.argsort(want[:, 0])])                  # rows intact
+dist.destroy_process_group()
+print("rank", rank, "ok", mine.shape[0])
+'''
+
+
+def test_two_rank_gloo_rebalance_moves_whole_rays(tmp_path):
+    """world_size 2 on CPU (gloo): the row exchange behind RayEnsemble.rebalance moves surplus rays, all fields of a ray
+    together, and every ray ends up on exactly one rank."""
+    script = tmp_path / "worker_rebalance.py"
+    script.write_text(_REBALANCE_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
     our arm's metric / unit / config, an e2e object without copies and the cpu_baseline that describes the run."""

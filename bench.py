@@ -550,6 +550,63 @@ def parity_check(args, rank, world, dist):
                "mean_flow_identical_on_all_ranks": bool(same),
                "oracle": "oracle port (pinned bit-for-bit to the Python reference for constant N; the N(z) terms are an extension "
                          "pinned to an independent numpy restatement), %d threads, %.1f s" % (host_threads(), time.perf_counter() - t0)}
+    del ens
+    # ---- phase 2: skewed deletion -> re-balancing over the ranks -> the driver loop with the fused post-step clamp ----
+    sc = scenarios.nz_sheared_ensemble(120_011, seed=78, amplitude=1.0) if args.workload == "c2" else \
+        scenarios.column_ensemble(120_011, seed=78, ngrid=1001, sheared=True, amplitude=1.0)
+    sc.state[1] = np.arange(sc.n, dtype=np.float64)          # lam is inert in column mode: it carries the ray's identity
+    b, e = shard_range(sc.n, rank, world)
+    ens = RayEnsemble([a[b:e] for a in sc.state], sc.dkk[b:e], sc.dll[b:e], sc.rr_mm_area[b:e], sc.uu, sc.vv, sc.grid, sc.grids,
+                      sc.rhobar, sc.pressure_gradient, bvf=sc.model["bvf"], phi0=sc.model["phi0"])
+    kept = ens.compact(sc.dt, float(np.quantile(np.abs(sc.state[7]), 0.2 if rank == 0 else 0.9)))    # rank 0 loses most of its rays
+    after = ens.rebalance()
+    ens.advance(sc.dt, 2, saturate=True)
+    mine = ens.to_var()
+    pack = ([mine[i] for i in range(11)], kept, after)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, pack)
+    else:
+        gathered = [pack]
+    if rank == 0:
+        import oracle
+        got = [np.concatenate([gathered[r][0][i] for r in range(world)]) for i in range(9)]
+        order = np.argsort(got[1])
+        sel = got[1][order].astype(np.int64)
+        counts, afters = [g[1] for g in gathered], [g[2] for g in gathered]
+        cfg = sc.oracle_cfg()
+        cfg.update(dkk=sc.dkk[sel], dll=sc.dll[sel], rr_mm_area=sc.rr_mm_area[sel])
+        orc = oracle.Oracle(cfg, nthreads=host_threads())
+        var = np.empty(11, dtype=object)
+        for i in range(9):
+            var[i] = sc.state[i][sel]
+        var[9], var[10] = sc.uu, sc.vv
+        start = [np.array(a) for a in var[:9]]
+        clamped = 0
+        for _ in range(2):
+            out = orc.RK3(sc.dt, var)
+            dens = orc.saturation(sc.dt, out[0], var[3], (out[3] - var[3]) / 1, var[4], (out[4] - var[4]) / sc.dt, out[5], out[6],
+                                  var[7], (out[7] - var[7]) / sc.dt, direct=True)
+            clamped += int(np.count_nonzero(dens != out[0]))
+            out[0] = dens
+            var = out
+        ray2, grid2 = 0.0, 0.0
+        for i in range(11):
+            if i >= 9:
+                scale = max(float(np.max(np.abs(var[i]))), 1e-300)
+                for r in range(world):
+                    grid2 = max(grid2, float(np.max(np.abs(gathered[r][0][i] - var[i]))) / scale)
+            else:
+                g = got[i][order]
+                scale = np.maximum(np.abs(var[i]), np.abs(var[i] - start[i]))
+                diff = np.abs(g - var[i])
+                ray2 = max(ray2, float(np.max(np.where(diff == 0, 0.0, diff / np.where(scale == 0, 1.0, scale)))))
+        ok2 = bool(len(np.unique(sel)) == len(sel) == sum(counts) == sum(afters) and max(afters) - min(afters) <= 1 and
+                   ray2 <= 1e-10 and grid2 <= 1e-10 and clamped > 0)
+        res["deletion_rebalance_advance"] = {"ok": ok2, "rays_before_deletion": sc.n, "survivors_per_rank": counts,
+                                             "after_rebalance": afters, "steps": 2, "rays_clamped": clamped,
+                                             "max_ray_rel_err": ray2, "max_grid_rel_err": grid2}
+        res["ok"] = bool(res["ok"] and ok2)
     if world > 1:
         flag = torch.tensor([1 if res["ok"] else 0], dtype=torch.int32, device="cuda")
         dist.broadcast(flag, 0)

@@ -27,13 +27,15 @@ __device__ __forceinline__ void shear_interp(double x, const double *__restrict_
     if (x <= xg[0]) { j = 0; flat = true; }
     else if (x >= xg[nc - 1]) { j = nc - 1; flat = true; }
     else { j = interp_locate(x, xg, nc, rdz); flat = false; }
-    const double fu0 = dvd(sub(uu[j + 1], uu[j]), dzg), fv0 = dvd(sub(vv[j + 1], vv[j]), dzg);
+    // divisions by the loop-invariant dz_grid in the exact invariant-divisor form (rdz = RN(1 / dzg); common.cuh)
+    const double fu0 = div_inv_safe(sub(uu[j + 1], uu[j]), dzg, rdz), fv0 = div_inv_safe(sub(vv[j + 1], vv[j]), dzg, rdz);
     const double dx = flat ? 0.0 : sub(x, xg[j]);
     if (flat || dx == 0.0) { du_ray = fu0; dv_ray = fv0; return; }
-    const double fu1 = dvd(sub(uu[j + 2], uu[j + 1]), dzg), fv1 = dvd(sub(vv[j + 2], vv[j + 1]), dzg);
+    const double fu1 = div_inv_safe(sub(uu[j + 2], uu[j + 1]), dzg, rdz), fv1 = div_inv_safe(sub(vv[j + 2], vv[j + 1]), dzg, rdz);
     const double w = sub(xg[j + 1], xg[j]);
-    du_ray = add(mul(dvd(sub(fu1, fu0), w), dx), fu0);
-    dv_ray = add(mul(dvd(sub(fv1, fv0), w), dx), fv0);
+    const double nu = sub(fu1, fu0), nv = sub(fv1, fv0);
+    du_ray = add(mul(w == dzg ? div_inv_safe(nu, dzg, rdz) : dvd(nu, w), dx), fu0);
+    dv_ray = add(mul(w == dzg ? div_inv_safe(nv, dzg, rdz) : dvd(nv, w), dx), fv0);
 }
 
 struct RhsArgs {
@@ -48,7 +50,11 @@ struct RhsArgs {
 // need_sat = false (the fused RK stage with saturate_online off) skips the saturation threshold, whose result the
 // reference multiplies by False (L:647): the tendency is then +0.0 instead of -0.0 where the threshold is exceeded,
 // which no state can tell apart.
-__device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9], double t[9], bool need_sat = true)
+// ff_out / cgr_out, if given, receive 2 Omega sin(phi) and cg_rr at the ray centre for the caller's deposit.
+// The divisions that share a divisor -- by RAD_EARTH + rr, om, |k|^2, cos(phi) -- go through SharedDiv (one refined
+// reciprocal per divisor, quotients bit-identical to the IEEE division).
+__device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9], double t[9], bool need_sat = true,
+                                        double *ff_out = nullptr, double *cgr_out = nullptr)
 {
     const msgwam_params_t &p = a.p;
     const int G = p.G;
@@ -76,36 +82,40 @@ __device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9]
     }
     double du_ray, dv_ray;
     shear_interp(rr, a.grid, a.uu, a.vv, G, p.dz_grid, p.inv_dz_grid, du_ray, dv_ray);
+    if (ff_out) *ff_out = ff;
+    if (cgr_out) *cgr_out = cgr;
     double cgl = 0.0, cgp = 0.0;
+    const SharedDiv by_om(om), by_vk(vk);
     if (p.hprop) {                                                            // L:400-405, 424-429
-        const double uu_ray = interp1(rr, a.grids, a.uu, G, p.inv_dz_grids);
-        const double vv_ray = interp1(rr, a.grids, a.vv, G, p.inv_dz_grids);
+        const double uu_ray = interp1_dz(rr, a.grids, a.uu, G, p.dz_grids, p.inv_dz_grids);
+        const double vv_ray = interp1_dz(rr, a.grids, a.vv, G, p.dz_grids, p.inv_dz_grids);
         const double nd = sub(n2, mul(om, om));
-        cgl = add(mul(dvd(dvd(kk, om), vk), nd), uu_ray);
-        cgp = add(mul(dvd(dvd(ll, om), vk), nd), vv_ray);
+        cgl = add(mul(by_vk(by_om(kk)), nd), uu_ray);
+        cgp = add(mul(by_vk(by_om(ll)), nd), vv_ray);
     }
     const double rad = add(p.rad_earth, rr);
+    const SharedDiv by_rad(rad), by_cphi(cphi);
     const double drr_st = mul(.5, add(cgr_down, cgr_up));                     // L:640
     const double ddrr_st = sub(cgr_up, cgr_down);                             // L:641
     double dkk_st = 0.0, dll_st = 0.0;
     if (p.hprop) {
         const double tphi = tan(phi);
         const double zero = add(mul(kk, 0.0), mul(ll, 0.0));
-        const double g_lam = dvd(dvd(zero, rad), cphi);                       // L:465
-        dkk_st = sub(mul(dvd(kk, rad), sub(mul(tphi, cgp), cgr)), g_lam);     // L:468-469
-        const double g_phi = dvd(zero, rad);                                  // L:489
+        const double g_lam = by_cphi(by_rad(zero));                           // L:465
+        dkk_st = sub(mul(by_rad(kk), sub(mul(tphi, cgp), cgr)), g_lam);       // L:468-469
+        const double g_phi = by_rad(zero);                                    // L:489
         const double df2 = mul(mul(mul(p.c8rot2, sphi), cphi), 1.0);          // L:491
-        const double t3 = mul(dvd(dvd(dvd(m2, 2.0), om), vk), df2);
+        const double t3 = mul(by_vk(by_om(mul(m2, .5))), df2);                // m2 / 2 == m2 * .5, exactly
         const double sum = add(add(mul(ll, cgr), mul(mul(kk, tphi), cgl)), t3);
-        dll_st = sub(dvd(-sum, rad), g_phi);                                  // L:494-497
+        dll_st = sub(by_rad(-sum), g_phi);                                    // L:494-497
     }
     const double g_rr = add(mul(kk, du_ray), mul(ll, dv_ray));                // L:517
-    double dmm_st = sub(dvd(add(mul(kk, cgl), mul(ll, cgp)), rad), g_rr);     // L:519-520
+    double dmm_st = sub(by_rad(add(mul(kk, cgl), mul(ll, cgp))), g_rr);       // L:519-520
     if (a.bvf != nullptr) {                                                   // ext: - N N' (k^2 + l^2) / om / |k|^2
         const double nr = interp1(rr, a.grids, a.bvf, G, p.inv_dz_grids);
         double dnr, unused;
         shear_interp(rr, a.grid, a.bvf, a.bvf, G, p.dz_grid, p.inv_dz_grid, dnr, unused);
-        dmm_st = sub(dmm_st, dvd(dvd(mul(mul(nr, dnr), kh2), om), vk));
+        dmm_st = sub(dmm_st, by_vk(by_om(mul(mul(nr, dnr), kh2))));
     }
     double st = 0.0;
     if (need_sat) {
@@ -116,8 +126,8 @@ __device__ __forceinline__ void ray_rhs(const RhsArgs &a, int64_t i, double x[9]
     }
     x[0] = dens; x[1] = lam; x[2] = phi; x[3] = rr; x[4] = drr; x[5] = kk; x[6] = ll; x[7] = mm; x[8] = dmm;
     t[0] = mul(p.saturate_online ? 1.0 : 0.0, st);                            // L:647
-    t[1] = use_ff ? 0.0 : dvd(dvd(cgl, rad), cphi);                           // L:638
-    t[2] = use_ff ? 0.0 : dvd(cgp, rad);                                      // L:639
+    t[1] = use_ff ? 0.0 : by_cphi(by_rad(cgl));                               // L:638
+    t[2] = use_ff ? 0.0 : by_rad(cgp);                                        // L:639
     t[3] = drr_st;
     t[4] = ddrr_st;
     t[5] = dkk_st;
@@ -344,7 +354,8 @@ __global__ void __launch_bounds__(NT, MSGWAM_STAGE_CTAS) stage_rays_kernel(const
             }
         }
         if (live) {
-            ray_rhs(a.r, i, x, t, p.saturate_online != 0);
+            double ff, cgr_c;
+            ray_rhs(a.r, i, x, t, p.saturate_online != 0, &ff, &cgr_c);
             // wave_projection(var = 0) of the same state, called as L:654-658
             const double hd = mul(.5, x[4]), hm = mul(.5, x[8]);
             rl = sub(x[3], hd); ru = add(x[3], hd);
@@ -352,18 +363,32 @@ __global__ void __launch_bounds__(NT, MSGWAM_STAGE_CTAS) stage_rays_kernel(const
             ok = cell_range(rl, ru, p.dz_grids, p.inv_dz_grids, ng - 2, nlow, nup);
             if (ok) {
                 psv = fabs(mul(mul(a.r.r.dkk[i], a.r.r.dll[i]), x[8]));           // L:137
-                const double ff = mul(p.two_rot, sin(x[2]));
-                const double n2 = n2_at(a.r.bvf, a.r.grids, ng, p.inv_dz_grids, p.n2, mul(.5, add(rl, ru)));
-                const double cgr = cg_rr_fast(add(mul(x[5], x[5]), mul(x[6], x[6])), mul(.5, add(ml, mu)), mul(ff, ff), n2);
+                // cg_rr at (.5 (m_low + m_up), .5 (r_low + r_up)): almost always bit-identical to the centre's arguments,
+                // then the right-hand side's value is reused (ff = 2 Omega sin(phi) is the same expression there)
+                const double mid = mul(.5, add(ml, mu)), zc = mul(.5, add(rl, ru));
+                double cgr = cgr_c;
+                if (mid != x[7] || (a.r.bvf != nullptr && zc != x[3])) {
+                    const double n2 = n2_at(a.r.bvf, a.r.grids, ng, p.inv_dz_grids, p.n2, zc);
+                    cgr = cg_rr_fast(add(mul(x[5], x[5]), mul(x[6], x[6])), mid, mul(ff, ff), n2);
+                }
                 v0 = mul(mul(cgr, x[5]), x[0]); v1 = mul(mul(cgr, x[6]), x[0]);   // L:148-149
             }
         }
         deposit_cells(ok, nlow, nup, rl, ru, psv, v0, v1, p.dz_grids, p.inv_dz_grids, g, win, h0, h1, SplitTargets{h0, h1, nullptr});
         if (live) {
+            // slots whose tendency is identically zero in this mode (L:638-645 with HPROP off: lam, phi, kk, ll; a scalar N:
+            // drr, dmm; saturate_online off: dens) keep their value: no low-storage traffic for them (their register stays
+            // the exact zero it would hold), and no store at all when the step runs in place
+            const double *const xin[9] = {a.r.r.dens, a.r.r.lam, a.r.r.phi, a.r.r.rr, a.r.r.drr, a.r.r.kk, a.r.r.ll, a.r.r.mm, a.r.r.dmm};
 #pragma unroll
             for (int f = 0; f < 9; ++f) {                                         // L:693-698
+                const bool moves = (f == 3 || f == 7) ? true : (f == 0) ? p.saturate_online != 0 : (f == 4 || f == 8) ? a.r.bvf != nullptr : p.hprop != 0;
+                if (!moves) {
+                    if (a.xo[f] != xin[f]) a.xo[f][i] = x[f];
+                    continue;
+                }
                 double qq;
-                if (a.stage == 0) { qq = mul(p.dt, t[f]); a.xo[f][i] = add(x[f], dvd(qq, 3.0)); }
+                if (a.stage == 0) { qq = mul(p.dt, t[f]); a.xo[f][i] = add(x[f], div_inv_safe(qq, 3.0, 1.0 / 3.0)); }   // qq / 3, exact
                 else { qq = sub(mul(p.dt, t[f]), mul(as, a.q[f][i])); a.xo[f][i] = add(x[f], mul(bs, qq)); }
                 a.q[f][i] = qq;
             }

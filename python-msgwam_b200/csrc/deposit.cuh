@@ -108,12 +108,34 @@ __device__ __forceinline__ double cell_weight(int c, double rl, double ru, doubl
 // Sums are exact in fixed point, hence independent of the order of the adds; the quantum 1 / scale is below 2^-58 of
 // the bound.  Contributions that do not fit (non-finite, or larger than the bound allows) go to the global deposit as
 // fp64 atomics, unscaled.
+// high word of q plus the carry out of old + low word: one add with carry-out, one add with carry-in
+__device__ __forceinline__ unsigned hi_plus_carry(unsigned old, unsigned lo, long long q)
+{
+    unsigned h;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(h) : "r"(old), "r"(lo), "r"((unsigned)(q >> 32)));
+    return h;
+}
+
 struct SplitTargets {
     double *s0, *s1; int *used;
-    double scale = 0.0, scale1 = 0.0;      // fixed-point scales of the two components (each has its own bound); 0: fp64 mode
+    double scale = 0.0, scale1 = 0.0;      // fixed-point scales of the two components (each has its own bound); 0: fp64 mode;
+                                           // negative (-1): the component's bound is exactly zero -- every contribution is
+                                           // an exact zero and nothing is added (a non-zero one would trip the bound check)
     double *g0 = nullptr, *g1 = nullptr;   // fixed-point mode: the global deposit rows, for contributions that do not fit
     __device__ __forceinline__ void mark() const { if (used != nullptr) *used = 1; }
     // both components of up to two cells in fixed point: the four low-word adds first, then the carries and high words
+    // one component of up to two cells (the other component is identically zero, see `scale`)
+    __device__ __forceinline__ void add2_fixed_one(double *row, int c0, double x0, bool two, int c1, double x1) const
+    {
+        const long long q0 = __double2ll_rn(x0), q2 = __double2ll_rn(x1);
+        unsigned *w0 = reinterpret_cast<unsigned *>(row + c0), *w2 = reinterpret_cast<unsigned *>(row + c1);
+        const unsigned l0 = (unsigned)q0, l2 = (unsigned)q2;
+        const unsigned o0 = atomicAdd(w0, l0);
+        unsigned o2 = 0;
+        if (two) o2 = atomicAdd(w2, l2);
+        atomicAdd(w0 + 1, hi_plus_carry(o0, l0, q0));
+        if (two) atomicAdd(w2 + 1, hi_plus_carry(o2, l2, q2));
+    }
     __device__ __forceinline__ void add2_fixed(int c0, double x0, double y0, bool two, int c1, double x1, double y1) const
     {
         const long long q0 = __double2ll_rn(x0), q1 = __double2ll_rn(y0), q2 = __double2ll_rn(x1), q3 = __double2ll_rn(y1);
@@ -123,11 +145,13 @@ struct SplitTargets {
         const unsigned o0 = atomicAdd(w0, l0), o1 = atomicAdd(w1, l1);
         unsigned o2 = 0, o3 = 0;
         if (two) { o2 = atomicAdd(w2, l2); o3 = atomicAdd(w3, l3); }
-        const unsigned h0 = (unsigned)(q0 >> 32) + ((o0 + l0) < l0), h1 = (unsigned)(q1 >> 32) + ((o1 + l1) < l1);
-        const unsigned h2 = (unsigned)(q2 >> 32) + ((o2 + l2) < l2), h3 = (unsigned)(q3 >> 32) + ((o3 + l3) < l3);
-        if (h0) atomicAdd(w0 + 1, h0);
-        if (h1) atomicAdd(w1 + 1, h1);
-        if (two) { if (h2) atomicAdd(w2 + 1, h2); if (h3) atomicAdd(w3 + 1, h3); }
+        const unsigned h0 = hi_plus_carry(o0, l0, q0), h1 = hi_plus_carry(o1, l1, q1);
+        const unsigned h2 = hi_plus_carry(o2, l2, q2), h3 = hi_plus_carry(o3, l3, q3);
+        // the high words are added unconditionally: with contributions of ~2^40 units a zero high word is rare, and
+        // a branch around each add costs four instructions (ISETP, BSSY, BRA, BSYNC)
+        atomicAdd(w0 + 1, h0);
+        atomicAdd(w1 + 1, h1);
+        if (two) { atomicAdd(w2 + 1, h2); atomicAdd(w3 + 1, h3); }
     }
     __device__ __forceinline__ void add(int c, double x, double y) const { atomicAdd(s0 + c, x); atomicAdd(s1 + c, y); }
     // Two cells at once, optimistically: the four read-add-CAS sequences are issued side by side so that their
@@ -165,6 +189,18 @@ __device__ __forceinline__ void deposit_fixed(int nlow, int nup, double rl, doub
 {
     if (fits) {
         sink.mark();
+        if (sink.scale < 0.0 || sink.scale1 < 0.0) {            // CTA-uniform: a component that is identically zero adds nothing
+            if (sink.scale < 0.0 && sink.scale1 < 0.0) return;
+            double *row = sink.scale1 < 0.0 ? sink.s0 : sink.s1;
+            const double w = sink.scale1 < 0.0 ? w0 : w1;
+            for (int c = nlow; c < nup; c += 2) {
+                const bool two = c + 1 < nup;
+                const int c1 = two ? c + 1 : c;
+                const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g), t1 = cell_weight(c1, rl, ru, psv, dz, rdz, g);
+                sink.add2_fixed_one(row, c, mul(t0, w), two, c1, mul(t1, w));
+            }
+            return;
+        }
         for (int c = nlow; c < nup; c += 2) {
             const bool two = c + 1 < nup;
             const int c1 = two ? c + 1 : c;
@@ -225,15 +261,14 @@ __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, doubl
             for (int c = lo; c < hi; ++c) {                     // warp-uniform trip count
                 const bool in = ok && c >= nlow && c < nup;
                 const double t = cell_weight(c, rl, ru, psv, dz, rdz, g);
-                const long long sx = warp_sum_i64(in ? __double2ll_rn(mul(t, w0)) : 0ll);
-                const long long sy = warp_sum_i64(in ? __double2ll_rn(mul(t, w1)) : 0ll);
-                if (lane < 2) {                                 // lane 0: first component, lane 1: second
+                const long long sx = sink.scale < 0.0 ? 0ll : warp_sum_i64(in ? __double2ll_rn(mul(t, w0)) : 0ll);
+                const long long sy = sink.scale1 < 0.0 ? 0ll : warp_sum_i64(in ? __double2ll_rn(mul(t, w1)) : 0ll);
+                if (lane < 2 && (lane ? sink.scale1 : sink.scale) > 0.0) {      // lane 0: first component, lane 1: second
                     const long long q = lane ? sy : sx;
                     unsigned *w = reinterpret_cast<unsigned *>((lane ? sink.s1 : sink.s0) + c);
                     const unsigned l = (unsigned)q;
                     const unsigned o = atomicAdd(w, l);
-                    const unsigned h = (unsigned)(q >> 32) + ((o + l) < l);
-                    if (h) atomicAdd(w + 1, h);
+                    atomicAdd(w + 1, hi_plus_carry(o, l, q));
                 }
             }
             if (lane == 0) sink.mark();

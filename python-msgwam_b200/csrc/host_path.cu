@@ -7,6 +7,8 @@
 // returns copies of the inputs for those slots and they are never moved over PCIe.
 #include "common.cuh"
 #include <string.h>
+#include <sched.h>
+#include <omp.h>
 
 extern "C" {
 
@@ -25,6 +27,72 @@ const char *msgwam_error_string(int code)
 }
 
 static inline int64_t pad32(int64_t n) { return (n + 31) & ~(int64_t)31; }
+
+// ---- uploads from PAGEABLE host arrays (what an unmodified driver script passes: rows of its history arrays, R:160-172)
+// cudaMemcpyAsync from pageable memory is a staged, blocking copy that the driver runs on one thread (~10-15 GB/s).
+// Large pageable arrays are instead copied by several host threads into one of two page-locked chunks, each of which
+// goes up with an asynchronous copy while the threads fill the other one: the upload then runs at the speed of the
+// host's memory system, up to the PCIe rate.  Page-locked (or registered) arrays are copied directly.
+namespace {
+constexpr size_t STAGE_CHUNK = (size_t)32 << 20;       // bytes per page-locked chunk
+struct Stager {
+    char *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int next = 0, threads = 1;
+    bool ok = false;
+    bool init()
+    {
+        if (ok) return true;
+        for (int k = 0; k < 2; ++k) {
+            if (cudaHostAlloc(reinterpret_cast<void **>(&buf[k]), STAGE_CHUNK, cudaHostAllocPortable) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        cpu_set_t set;
+        int n = 1;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);     // not OMP_NUM_THREADS: torchrun sets it to 1
+        threads = n < 1 ? 1 : (n > 8 ? 8 : n);
+        ok = true;
+        return true;
+    }
+} g_stager;
+
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+int upload(double *dst, const double *src, int64_t cnt, cudaStream_t s)
+{
+    if (cnt <= 0) return 0;
+    if (!src) return MSGWAM_E_BADARG;
+    const size_t bytes = (size_t)cnt * sizeof(double);
+    if (bytes < ((size_t)4 << 20) || !is_pageable(src) || !g_stager.init())
+        return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+    const char *from = reinterpret_cast<const char *>(src);
+    char *to = reinterpret_cast<char *>(dst);
+    for (size_t off = 0; off < bytes; off += STAGE_CHUNK) {
+        const size_t len = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+        const int k = g_stager.next;
+        g_stager.next ^= 1;
+        cudaError_t e = cudaEventSynchronize(g_stager.ev[k]);          // the chunk's previous upload has left it
+        if (e != cudaSuccess) return (int)e;
+        const int T = g_stager.threads;
+        const size_t per = ((len + T - 1) / T + 63) & ~(size_t)63;
+#pragma omp parallel for num_threads(T) schedule(static)
+        for (int t = 0; t < T; ++t) {
+            const size_t b = (size_t)t * per;
+            if (b < len) memcpy(g_stager.buf[k] + b, from + off + b, b + per <= len ? per : len - b);
+        }
+        e = cudaMemcpyAsync(to + off, g_stager.buf[k], len, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaEventRecord(g_stager.ev[k], s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+}  // namespace
 
 // Page-locked staging for the grid-sized arguments of msgwam_rk3_column_host (one block per process, portable across
 // the process's devices, grown on demand;
@@ -92,11 +160,8 @@ static int rk3_column_host_impl(const msgwam_params_t *p, int64_t n, const doubl
     cudaError_t e;
 #define MW_H2D(dst, src, cnt)                                                                          \
     do {                                                                                               \
-        if ((cnt) > 0) {                                                                               \
-            if (!(src)) return MSGWAM_E_BADARG;                                                        \
-            e = cudaMemcpyAsync((dst), (src), (size_t)(cnt) * sizeof(double), cudaMemcpyHostToDevice, s); \
-            if (e != cudaSuccess) return (int)e;                                                       \
-        }                                                                                              \
+        const int rc_up = upload((dst), (src), (cnt), s);     /* staged through page-locked chunks if pageable */ \
+        if (rc_up) return rc_up;                                                                       \
     } while (0)
     // The grid-sized inputs are ordinary (pageable) numpy arrays: six cudaMemcpyAsync calls from pageable memory are
     // six staged, blocking copies (~100 us in all).  They are gathered into one page-locked block laid out like the

@@ -215,27 +215,14 @@ __device__ __forceinline__ void deposit_fixed(int nlow, int nup, double rl, doub
     }
 }
 
-// warp sum of 64-bit integers (two's complement, modulo 2^64): REDUX.SUM is a 32-bit operation, so the value travels
-// as three limbs of 21 + 21 + 22 bits whose 32-fold sums cannot overflow
-__device__ __forceinline__ long long warp_sum_i64(long long q)
-{
-    const unsigned long long u = (unsigned long long)q;
-    const unsigned s0 = __reduce_add_sync(FULL_MASK, (unsigned)(u & 0x1fffffu));
-    const unsigned s1 = __reduce_add_sync(FULL_MASK, (unsigned)((u >> 21) & 0x1fffffu));
-    const unsigned s2 = __reduce_add_sync(FULL_MASK, (unsigned)(u >> 42));
-    return (long long)((unsigned long long)s0 + ((unsigned long long)s1 << 21) + ((unsigned long long)s2 << 42));
-}
-
-constexpr int COHERENT_CELLS = 6;    // a warp whose ray volumes lie within this many cells sums them with warp reductions
-
-// Window-free deposit of the fused column sweeps (all 32 lanes must call): every lane adds its ray volume's overlap
-// weights (L:156-163) to the CTA histogram -- in fixed point when the deposit bound is known (the normal case), else
-// with fp64 compare-and-swap atomics (correct for any input, slow when the lanes of a warp share cells).
-// Fixed point: lanes that hit DIFFERENT cells add with native atomics at full rate, but 32 lanes on one address
-// serialise; a warp whose volumes all lie within COHERENT_CELLS cells (an ordered ensemble, a pile-up in one layer)
-// therefore sums each cell's 32 contributions with integer warp reductions -- exact, like everything in fixed point --
-// and two lanes add the totals.  Either way the result does not depend on the order of the rays, and neither path
-// depends on the other's locality: the cost of the deposit is flat from fully ordered to fully shuffled ensembles.
+// Window-free deposit of the fused column sweeps: every lane adds its ray volume's overlap weights (L:156-163) to the CTA
+// histogram -- in fixed point when the deposit bound is known (the normal case), else with fp64 compare-and-swap atomics
+// (correct for any input, slow when the lanes of a warp share cells).  In fixed point the result does not depend on
+// the order of the rays, and the cost barely does: measured per step at 1e7 rays, 0.63 ms for a dispersed or shuffled
+// ensemble against 0.79 ms when all 32 lanes of every warp hit the same cells (an exactly ordered ensemble).
+// (Measured and removed: summing a coherent warp's contributions per cell with integer warp reductions -- REDUX.SUM on
+// three 21-bit limbs, exact -- before two lanes add the totals: 6 REDUX per cell cost more than the 32 colliding atomics
+// they replace; a 5e7-ray pile-up in 67 cells ran at 10.7 ms per step that way and runs at 3.2 ms without.)
 // bx, by: this thread's running sums of the scaled |contributions| of the two components -- what the next step's deposit
 // bounds are made of (column_step.cu: publish_bounds); single precision is plenty for a bound with a margin of 8.
 template <class Sink>
@@ -250,30 +237,6 @@ __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, doubl
         const double f0 = mul(psv, fabs(w0)), f1 = mul(psv, fabs(w1));
         const bool fits = add(f0, f1) < 2.0e18;
         bx += ok ? __double2float_ru(f0) : 0.f; by += ok ? __double2float_ru(f1) : 0.f;
-        const int lo = __reduce_min_sync(FULL_MASK, ok ? nlow : INT_MAX);
-        if (lo == INT_MAX) return;                              // no lane has anything to deposit
-        const int hi = __reduce_max_sync(FULL_MASK, ok ? nup : INT_MIN);
-        // coherent: the warp's volumes lie within a few cells AND at least half of them start in the same cell (then the
-        // per-lane atomics would serialise); lanes merely close to each other are better off with their own atomics
-        const bool coherent = hi - lo <= COHERENT_CELLS && 2 * __popc(__ballot_sync(FULL_MASK, ok && nlow == lo)) >= 32;
-        if (coherent && __all_sync(FULL_MASK, !ok || fits)) {
-            const int lane = threadIdx.x & 31;
-            for (int c = lo; c < hi; ++c) {                     // warp-uniform trip count
-                const bool in = ok && c >= nlow && c < nup;
-                const double t = cell_weight(c, rl, ru, psv, dz, rdz, g);
-                const long long sx = sink.scale < 0.0 ? 0ll : warp_sum_i64(in ? __double2ll_rn(mul(t, w0)) : 0ll);
-                const long long sy = sink.scale1 < 0.0 ? 0ll : warp_sum_i64(in ? __double2ll_rn(mul(t, w1)) : 0ll);
-                if (lane < 2 && (lane ? sink.scale1 : sink.scale) > 0.0) {      // lane 0: first component, lane 1: second
-                    const long long q = lane ? sy : sx;
-                    unsigned *w = reinterpret_cast<unsigned *>((lane ? sink.s1 : sink.s0) + c);
-                    const unsigned l = (unsigned)q;
-                    const unsigned o = atomicAdd(w, l);
-                    atomicAdd(w + 1, hi_plus_carry(o, l, q));
-                }
-            }
-            if (lane == 0) sink.mark();
-            return;
-        }
         if (ok) deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, w0, w1, fits, dz, rdz, g, sink);
         return;
     }

@@ -19,7 +19,8 @@ def timed(ens, dt, k, fl):
 out = []
 cases = [("const1e6", lambda: scenarios.column_ensemble(1_000_000, seed=1234, ngrid=1001), True),
          ("const1e7", lambda: scenarios.column_ensemble(10_000_000, seed=1234, ngrid=1001), False),
-         ("nz1.25e7", lambda: scenarios.nz_sheared_ensemble(12_500_000, seed=1234), False)]
+         ("nz1.25e7", lambda: scenarios.nz_sheared_ensemble(12_500_000, seed=1234), False),
+         ("pileup2e7", lambda: scenarios.critical_level_ensemble(20_000_000, ngrid=1001, stress=True), False)]
 for name, mk, fl in cases:
     if which != "all" and which not in name: continue
     sc = mk(); ens = RayEnsemble.from_scenario(sc); del sc.state

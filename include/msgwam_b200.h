@@ -78,8 +78,11 @@ typedef struct msgwam_rays {
                             valid (zero the 16 doubles when the store is created or edited from outside, or call
                             msgwam_column_bounds).  With valid bounds the CTA histogram of the deposit accumulates in
                             64-bit fixed point with native integer atomics (deposit.cuh); NULL or invalid: fp64
-                            compare-and-swap atomics.  A bound that grows more than 8-fold within one step sets the
-                            error word (code 3).                                                                    */
+                            compare-and-swap atomics.  Stale bounds cost precision and speed, never correctness: a thread
+                            adds to the histogram only while the running sum of its scaled contributions is below 2^62 /
+                            (threads per CTA), so no accumulator can overflow; past that, and for non-finite rays,
+                            contributions go to the global deposit in fp64, and so do non-zero contributions of a
+                            component whose bound was exactly zero.                                                  */
 } msgwam_rays_t;
 
 /* Background profiles on the 1-D mean-flow grid (L:6-9). */

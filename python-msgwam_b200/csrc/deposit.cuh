@@ -119,9 +119,10 @@ __device__ __forceinline__ unsigned hi_plus_carry(unsigned old, unsigned lo, lon
 struct SplitTargets {
     double *s0, *s1; int *used;
     double scale = 0.0, scale1 = 0.0;      // fixed-point scales of the two components (each has its own bound); 0: fp64 mode;
-                                           // negative (-1): the component's bound is exactly zero -- every contribution is
-                                           // an exact zero and nothing is added (a non-zero one would trip the bound check)
+                                           // negative (-1): the component's bound is exactly zero -- its contributions were
+                                           // all exact zeros, which add nothing (non-zero ones go to g0 / g1 in fp64)
     double *g0 = nullptr, *g1 = nullptr;   // fixed-point mode: the global deposit rows, for contributions that do not fit
+    float lim = 1.0e15f;                   // fixed-point mode: a thread adds to the histogram while its running sums stay below
     __device__ __forceinline__ void mark() const { if (used != nullptr) *used = 1; }
     // both components of up to two cells in fixed point: the four low-word adds first, then the carries and high words
     // one component of up to two cells (the other component is identically zero, see `scale`)
@@ -189,10 +190,20 @@ __device__ __forceinline__ void deposit_fixed(int nlow, int nup, double rl, doub
 {
     if (fits) {
         sink.mark();
-        if (sink.scale < 0.0 || sink.scale1 < 0.0) {            // CTA-uniform: a component that is identically zero adds nothing
-            if (sink.scale < 0.0 && sink.scale1 < 0.0) return;
-            double *row = sink.scale1 < 0.0 ? sink.s0 : sink.s1;
-            const double w = sink.scale1 < 0.0 ? w0 : w1;
+        if (sink.scale < 0.0 || sink.scale1 < 0.0) {            // CTA-uniform: a component whose bound is exactly zero
+            // Its contributions were all exact zeros in the previous step; exact zeros add nothing, and should a ray
+            // bring a non-zero one now (it re-entered the deposit domain, say) it goes to the global deposit in fp64.
+            const bool zx = sink.scale < 0.0, zy = sink.scale1 < 0.0;
+            if ((zx && v0 != 0.0) || (zy && v1 != 0.0)) {
+                for (int c = nlow; c < nup; ++c) {
+                    const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g);
+                    if (zx && v0 != 0.0) atomicAdd(sink.g0 + c, mul(t0, v0));
+                    if (zy && v1 != 0.0) atomicAdd(sink.g1 + c, mul(t0, v1));
+                }
+            }
+            if (zx && zy) return;
+            double *row = zy ? sink.s0 : sink.s1;
+            const double w = zy ? w0 : w1;
             for (int c = nlow; c < nup; c += 2) {
                 const bool two = c + 1 < nup;
                 const int c1 = two ? c + 1 : c;
@@ -232,11 +243,15 @@ __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, doubl
 {
     ok = ok && (nup > nlow);
     if (sink.scale != 0.0) {                                    // CTA-uniform
-        // A cell weight is at most psv (1 + 2^-52): the ray fits if psv * |v| * scale stays far below 2^63.
+        // A cell weight is at most psv (1 + 2^-52), so f0, f1 bound what this ray adds to any cell.  The thread's running
+        // sums bx, by of them double as an overflow guard: a ray goes to the histogram only while both are below
+        // sink.lim = 2^62 / (threads per CTA) -- then no cell of the CTA histogram can reach 2^63, whatever has become of
+        // the bounds the scales were derived from; with accurate bounds a thread ends a sweep a factor 16 below the limit.
+        // Past it (stale bounds, a non-finite ray) contributions go to the global deposit in fp64.
         const double w0 = mul(v0, sink.scale), w1 = mul(v1, sink.scale1);
         const double f0 = mul(psv, fabs(w0)), f1 = mul(psv, fabs(w1));
-        const bool fits = add(f0, f1) < 2.0e18;
         bx += ok ? __double2float_ru(f0) : 0.f; by += ok ? __double2float_ru(f1) : 0.f;
+        const bool fits = (sink.scale < 0.0 || bx < sink.lim) && (sink.scale1 < 0.0 || by < sink.lim);
         if (ok) deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, w0, w1, fits, dz, rdz, g, sink);
         return;
     }
@@ -314,7 +329,7 @@ __device__ __forceinline__ void deposit_cells(bool ok, int nlow, int nup, double
         // outlier lane / unordered rays: add to the CTA histogram directly
         if (sink.scale != 0.0) {
             const double w0 = mul(v0, sink.scale), w1 = mul(v1, sink.scale1);
-            deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, w0, w1, mul(psv, add(fabs(w0), fabs(w1))) < 2.0e18, dz, rdz, g, sink);
+            deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, w0, w1, mul(psv, add(fabs(w0), fabs(w1))) < sink.lim, dz, rdz, g, sink);
             return;
         }
         sink.mark();

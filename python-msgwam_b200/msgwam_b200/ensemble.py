@@ -372,9 +372,7 @@ class RayEnsemble:
             self._bounds.zero_()
             self._slab_version = None               # the next step measures the deposit bounds anew
             what = {1.0: "a peer did not deliver its deposit (the bounded wait of the peer-memory all-reduce timed out)",
-                    2.0: "the mean-flow slices of pass B did not all arrive in time (its CTAs were not co-resident)",
-                    3.0: "the deposited flux grew more than 8-fold within one step, beyond what the fixed-point histogram of "
-                         "the deposit was scaled for"}.get(word, "code %g" % word)
+                    2.0: "the mean-flow slices of pass B did not all arrive in time (its CTAs were not co-resident)"}.get(word, "code %g" % word)
             raise _cabi.MsgwamError("device-side check failed: %s; the results since the last check are invalid" % what)
 
     def check_errors(self):

@@ -192,14 +192,14 @@ def test_compaction_reads_any_non_zero_flag_byte_as_keep():
 
 @pytest.mark.parametrize("profile", [False, True])
 def test_fixed_point_histogram_bounds_protocol(profile):
-    """The CTA histogram of the deposit accumulates in 64-bit fixed point once the previous step has measured a bound of
-    the deposited flux (msgwam_rays_t.bounds): the first step of an ensemble runs the fp64 path and leaves bounds > 0;
-    later steps stay within the grid tolerance on a shuffled (all lanes outliers) ensemble; an edit of the store
-    through torch resets the bounds; a flux that grows more than 8-fold behind the ensemble's back raises."""
-    from msgwam_b200 import _cabi
+    """The CTA histogram of the deposit accumulates in 64-bit fixed point, scaled by bounds of the deposited flux
+    (msgwam_rays_t.bounds): before the first step of an ensemble a pre-pass measures them, every step leaves the bounds
+    of its own deposits; steps stay within the grid tolerance on a shuffled ensemble; an edit of the store through torch
+    triggers a new pre-pass; and a flux that grows 20-fold BEHIND the ensemble's back (stale bounds) still gives the
+    right answer -- rays that no longer fit the scale go to the global deposit in fp64, no accumulator can overflow."""
     from msgwam_b200.ensemble import RayEnsemble
     mk = scenarios.nz_sheared_ensemble if profile else (lambda n, **kw: scenarios.column_ensemble(n, ngrid=1001, sheared=True, **kw))
-    sc = mk(150_007, seed=21, amplitude=0.3, shuffled=True)
+    sc = mk(150_007, seed=21, amplitude=0.02, shuffled=True)    # 0.02 -> 0.09 -> 0.4 after the two edits below: never chaotic
     ens = RayEnsemble.from_scenario(sc)
     assert float(ens._bounds.abs().sum()) == 0.0
     ens.step(sc.dt)
@@ -211,21 +211,22 @@ def test_fixed_point_histogram_bounds_protocol(profile):
     for _ in range(4):
         want = orc.RK3(sc.dt, want)
     assert_state_close(ens.to_var(), want, ray_tol=1e-12, grid_tol=1e-11, tag="fixed point", start=sc.var())
-    # an edit through torch invalidates the bounds: the next step measures them again and the result stays right
+    # an edit through torch invalidates the bounds: the next step measures them again
     ens.field("dens").mul_(20.0)
+    want[0] = want[0] * 20.0
     ens.step(sc.dt)
+    want = orc.RK3(sc.dt, want)
     b2 = ens._bounds.cpu().numpy()
     assert np.all(b2[:6] > 10.0 * b1[:6]), (b1, b2)
-    ens.check_errors()
-    # the same growth behind the ensemble's back (version counter restored by hand): the step flags it
+    assert_state_close(ens.to_var(), want, ray_tol=1e-11, grid_tol=1e-10, tag="after an edit", start=sc.var())
+    # the same growth behind the ensemble's back (version counter restored by hand: no pre-pass, stale bounds)
     ens.field("dens").mul_(20.0)
+    want[0] = want[0] * 20.0
     ens._slab_version = ens._slab._version
-    ens.step(sc.dt)
-    with pytest.raises(_cabi.MsgwamError):
-        ens.check_errors()
-    ens.step(sc.dt, 2)                                          # bounds were reset: usable again
+    ens.step(sc.dt, 2)
+    want = orc.RK3(sc.dt, orc.RK3(sc.dt, want))
     ens.check_errors()
-    assert np.isfinite(ens.to_var()[9]).all()
+    assert_state_close(ens.to_var(), want, ray_tol=1e-10, grid_tol=1e-10, tag="stale bounds", start=sc.var())
 
 
 @pytest.mark.parametrize("profile,amplitude", [(False, 1.0), (True, 1.0), (True, 0.05)])

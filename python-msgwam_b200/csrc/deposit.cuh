@@ -235,7 +235,7 @@ __device__ __forceinline__ void deposit_fixed(int nlow, int nup, double rl, doub
 // three 21-bit limbs, exact -- before two lanes add the totals: 6 REDUX per cell cost more than the 32 colliding atomics
 // they replace; a 5e7-ray pile-up in 67 cells ran at 10.7 ms per step that way and runs at 3.2 ms without.)
 // bx, by: this thread's running sums of the scaled |contributions| of the two components -- what the next step's deposit
-// bounds are made of (column_step.cu: publish_bounds); single precision is plenty for a bound with a margin of 8.
+// bounds are made of (column_step.cu: publish_bounds); single precision is plenty for a bound with a factor 8 of headroom.
 template <class Sink>
 __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, double rl, double ru, double psv, double v0,
                                                double v1, double dz, double rdz, const double *__restrict__ g,

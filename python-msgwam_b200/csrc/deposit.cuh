@@ -235,7 +235,7 @@ __device__ __forceinline__ void deposit_fixed(int nlow, int nup, double rl, doub
 // three 21-bit limbs, exact -- before two lanes add the totals: 6 REDUX per cell cost more than the 32 colliding atomics
 // they replace; a 5e7-ray pile-up in 67 cells ran at 10.7 ms per step that way and runs at 3.2 ms without.)
 // bx, by: this thread's running sums of the scaled |contributions| of the two components -- what the next step's deposit
-// bounds are made of (column_step.cu: publish_bounds); single precision is plenty for a bound with a factor 8 of headroom.
+// bounds are made of (column_step.cu: publish_bounds); single precision is plenty for a bound with a factor 32 of headroom.
 template <class Sink>
 __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, double rl, double ru, double psv, double v0,
                                                double v1, double dz, double rdz, const double *__restrict__ g,
@@ -246,7 +246,7 @@ __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, doubl
         // A cell weight is at most psv (1 + 2^-52), so f0, f1 bound what this ray adds to any cell.  The thread's running
         // sums bx, by of them double as an overflow guard: a ray goes to the histogram only while both are below
         // sink.lim = 2^62 / (threads per CTA) -- then no cell of the CTA histogram can reach 2^63, whatever has become of
-        // the bounds the scales were derived from; with accurate bounds a thread ends a sweep a factor 16 below the limit.
+        // the bounds the scales were derived from; with accurate bounds the average thread ends a sweep a factor 64 below the limit.
         // Past it (stale bounds, a non-finite ray) contributions go to the global deposit in fp64.
         const double w0 = mul(v0, sink.scale), w1 = mul(v1, sink.scale1);
         const double f0 = mul(psv, fabs(w0)), f1 = mul(psv, fabs(w1));

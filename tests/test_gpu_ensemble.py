@@ -167,13 +167,14 @@ def test_driver_loop_on_the_device_vs_reference_history():
         assert np.array_equal(a.field(nm).cpu().numpy(), b.field(nm).cpu().numpy())
 
 
-@pytest.mark.parametrize("amplitude,steps,tol", [(8.0, 1, 2e-11), (1.0, 3, 1e-10)])
+@pytest.mark.parametrize("amplitude,steps,tol", [(8.0, 1, 1e-10), (1.0, 3, 1e-10)])
 def test_post_step_clamp_when_the_packet_saturates(amplitude, steps, tol):
     """The driver's packet never reaches saturation, so the clamp is exercised here: ensembles at and far above the
     static-instability amplitude, driver loop on the device vs the same loop through the oracle (R:157-188).  At eight
     times the threshold two thirds of the rays are clamped and the flow is violently unstable (wavenumbers change sign
     within a step; any 1e-16 difference grows ~1e3-fold per step, in the host-call loop just the same), hence one step
-    (the deposit's fixed-point sums differ from the oracle's sequential fp64 sums by a few 1e-14 of the grid fields)."""
+    (the deposit's fixed-point sums differ from the oracle's sequential fp64 sums by a few 1e-14 of the grid fields; the
+    contract tolerance of 1e-10 is what is asserted)."""
     from helpers import max_rel
     from msgwam_b200.ensemble import RayEnsemble
     sc = scenarios.column_ensemble(30011, seed=41, ngrid=401, sheared=True, amplitude=amplitude)

@@ -220,6 +220,11 @@ int msgwam_set_peer_timeout(double seconds);
 /* measurement hook: while `event` (a cudaEvent_t) is set, every fused column step records it between its two
  * launches so that the sweeps can be timed separately; NULL switches it off */
 int msgwam_debug_mid_event(void *event);
+/* test hook: launch every sweep with mult (1..8) CTAs per SM instead of one.  A CTA of a sweep fills an SM, so with
+ * mult > 1 most CTAs of a grid are not resident while the first ones run -- what kernels of other streams or MPS
+ * clients do to a grid -- and the step must complete with the same results: no kernel of this library waits on a
+ * CTA that has not started (the mean-flow chain hands its slices out by ticket).  1 = product configuration. */
+int msgwam_debug_grid_mult(int mult);
 
 /* single GPU: two launches -- the mean-flow chain and the finish run as the tails of the sweeps, in the last
  * CTA to retire */

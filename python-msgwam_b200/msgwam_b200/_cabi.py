@@ -77,6 +77,7 @@ SIGNATURES = {
     "msgwam_column_advance": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 8 + [ctypes.POINTER(Peers), _vp]),
     "msgwam_column_advance_nz": (ctypes.c_int, [_PP, _RP, _i64, _GP] + [_vp] * 10 + [ctypes.POINTER(Peers), _vp]),
     "msgwam_debug_mid_event": (ctypes.c_int, [_vp]),
+    "msgwam_debug_grid_mult": (ctypes.c_int, [ctypes.c_int]),
     "msgwam_column_step": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msgwam_debug_cg_rr_fast": (ctypes.c_int, [_vp, _vp, _vp, _vp, _dbl, _vp, _i64, _vp]),
     "msgwam_rhs_rays": (ctypes.c_int, [_PP, _RP, _i64, _GP, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp]),

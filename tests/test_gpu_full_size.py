@@ -229,6 +229,29 @@ def test_fixed_point_histogram_bounds_protocol(profile):
     assert_state_close(ens.to_var(), want, ray_tol=1e-10, grid_tol=1e-10, tag="stale bounds", start=sc.var())
 
 
+@pytest.mark.parametrize("profile", [False, True])
+def test_step_does_not_need_all_ctas_resident(profile):
+    """the mean-flow chain of the second sweep waits on a grid-wide arrival counter; that must not assume that
+    every CTA of the grid is resident (kernels of other streams or MPS clients may hold SMs).  With the test hook
+    msgwam_debug_grid_mult(3) every sweep is launched with three CTAs per SM, of which one fits: two thirds of the grid
+    have not started while the first third waits for the chain.  The slices of the chain are handed out by ticket to
+    whichever CTAs run, so the steps complete, the error word stays clear and the result is the oracle's."""
+    from msgwam_b200 import _cabi
+    from msgwam_b200.ensemble import RayEnsemble
+    mk = scenarios.nz_sheared_ensemble if profile else (lambda n, **kw: scenarios.column_ensemble(n, ngrid=1001, sheared=True, **kw))
+    sc = mk(300_011, seed=5, amplitude=0.3)
+    orc = oracle.Oracle(sc.oracle_cfg(), nthreads=oracle.max_threads())
+    want = orc.RK3(sc.dt, orc.RK3(sc.dt, sc.var()))
+    assert _cabi.lib.msgwam_debug_grid_mult(3) == 0
+    try:
+        ens = RayEnsemble.from_scenario(sc)
+        ens.step(sc.dt, 2)
+        got = ens.to_var()                      # synchronises and raises on a set error word (code 2: chain wait timed out)
+    finally:
+        assert _cabi.lib.msgwam_debug_grid_mult(1) == 0
+    assert_state_close(got, want, ray_tol=1e-12, grid_tol=1e-11, tag="3 CTAs per SM", start=sc.var())
+
+
 @pytest.mark.parametrize("profile,amplitude", [(False, 1.0), (True, 1.0), (True, 0.05)])
 def test_fused_advance_matches_the_driver_loop_through_the_oracle(profile, amplitude):
     """RayEnsemble.advance in the column modes = msgwam_column_advance / _nz: the RK3 step with the driver's post-step

@@ -123,7 +123,11 @@ struct SplitTargets {
                                            // all exact zeros, which add nothing (non-zero ones go to g0 / g1 in fp64)
     double *g0 = nullptr, *g1 = nullptr;   // fixed-point mode: the global deposit rows, for contributions that do not fit
     float lim = 1.0e15f;                   // fixed-point mode: a thread adds to the histogram while its running sums stay below
+    int mode = -1;                         // fx_mode(scale, scale1), worked out once per CTA by the column sweeps (-1: look at the scales)
     __device__ __forceinline__ void mark() const { if (used != nullptr) *used = 1; }
+    // 0: fp64 histogram; 1: both components in fixed point; 2: fixed point with a component whose bound is exactly zero
+    static __device__ __forceinline__ int fx_mode(double sc, double sc1) { return sc == 0.0 ? 0 : (sc < 0.0 || sc1 < 0.0) ? 2 : 1; }
+    __device__ __forceinline__ int get_mode() const { return mode >= 0 ? mode : fx_mode(scale, scale1); }
     // both components of up to two cells in fixed point: the four low-word adds first, then the carries and high words
     // one component of up to two cells (the other component is identically zero, see `scale`)
     __device__ __forceinline__ void add2_fixed_one(double *row, int c0, double x0, bool two, int c1, double x1) const
@@ -189,8 +193,8 @@ __device__ __forceinline__ void deposit_fixed(int nlow, int nup, double rl, doub
                                               double dz, double rdz, const double *__restrict__ g, const Sink &sink)
 {
     if (fits) {
-        sink.mark();
-        if (sink.scale < 0.0 || sink.scale1 < 0.0) {            // CTA-uniform: a component whose bound is exactly zero
+        if (sink.mode < 0) sink.mark();                         // the column sweeps mark the histogram once per CTA
+        if (sink.get_mode() == 2) {                             // CTA-uniform: a component whose bound is exactly zero
             // Its contributions were all exact zeros in the previous step; exact zeros add nothing, and should a ray
             // bring a non-zero one now (it re-entered the deposit domain, say) it goes to the global deposit in fp64.
             const bool zx = sink.scale < 0.0, zy = sink.scale1 < 0.0;
@@ -242,7 +246,8 @@ __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, doubl
                                                const Sink &sink, float &bx, float &by)
 {
     ok = ok && (nup > nlow);
-    if (sink.scale != 0.0) {                                    // CTA-uniform
+    const int mode = sink.get_mode();
+    if (mode != 0) {                                            // CTA-uniform
         // A cell weight is at most psv (1 + 2^-52), so f0, f1 bound what this ray adds to any cell.  The thread's running
         // sums bx, by of them double as an overflow guard: a ray goes to the histogram only while both are below
         // sink.lim = 2^62 / (threads per CTA) -- then no cell of the CTA histogram can reach 2^63, whatever has become of
@@ -251,7 +256,8 @@ __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, doubl
         const double w0 = mul(v0, sink.scale), w1 = mul(v1, sink.scale1);
         const double f0 = mul(psv, fabs(w0)), f1 = mul(psv, fabs(w1));
         bx += ok ? __double2float_ru(f0) : 0.f; by += ok ? __double2float_ru(f1) : 0.f;
-        const bool fits = (sink.scale < 0.0 || bx < sink.lim) && (sink.scale1 < 0.0 || by < sink.lim);
+        const bool fits = mode == 1 ? (bx < sink.lim && by < sink.lim)
+                                    : (sink.scale < 0.0 || bx < sink.lim) && (sink.scale1 < 0.0 || by < sink.lim);
         if (ok) deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, w0, w1, fits, dz, rdz, g, sink);
         return;
     }

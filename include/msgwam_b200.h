@@ -74,7 +74,9 @@ typedef struct msgwam_rays {
     double *bounds;      /* column mode only, may be NULL: 16 doubles of per-ensemble state that live next to a ray store
                             which is advanced IN PLACE.  [0..5] = for the deposits D0, D1, D2 of the previous step and
                             each of their two flux components, the max over CTAs of the sum of |contribution| over the
-                            CTA's rays; [6..11] = the same, being gathered by the running step; [12] = 1.0 when [0..5] are
+                            CTA's rays (D0 and D1, the two deposits of the first sweep, share their scales -- the larger
+                            of their bounds counts -- and are measured together, half of the sum to each);
+                            [6..11] = the same, being gathered by the running step; [12] = 1.0 when [0..5] are
                             valid (zero the 16 doubles when the store is created or edited from outside, or call
                             msgwam_column_bounds).  With valid bounds the CTA histogram of the deposit accumulates in
                             64-bit fixed point with native integer atomics (deposit.cuh); NULL or invalid: fp64

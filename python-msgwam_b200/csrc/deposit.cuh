@@ -208,19 +208,24 @@ __device__ __forceinline__ void deposit_fixed(int nlow, int nup, double rl, doub
             if (zx && zy) return;
             double *row = zy ? sink.s0 : sink.s1;
             const double w = zy ? w0 : w1;
-            for (int c = nlow; c < nup; c += 2) {
+            for (int c = nlow; c < nup; c += 2) {                  // see the two-component loop below
                 const bool two = c + 1 < nup;
-                const int c1 = two ? c + 1 : c;
-                const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g), t1 = cell_weight(c1, rl, ru, psv, dz, rdz, g);
-                sink.add2_fixed_one(row, c, mul(t0, w), two, c1, mul(t1, w));
+                const double ga = g[c], gb = g[c + 1], gc = g[c + 2];
+                const double t0 = mul(div_inv(fabs(sub(dmin(gb, ru), dmax(ga, rl))), dz, rdz), psv);
+                const double t1 = mul(div_inv(fabs(sub(dmin(gc, ru), dmax(gb, rl))), dz, rdz), psv);
+                sink.add2_fixed_one(row, c, mul(t0, w), two, c + 1, mul(t1, w));
             }
             return;
         }
         for (int c = nlow; c < nup; c += 2) {
+            // cells c and c + 1 share the node between them; without a second cell (`two` false: its adds are
+            // predicated off) the weight of [g[c + 1], g[c + 2]] is computed and dropped (c + 2 <= nup + 1 <= G - 1: cell_range
+            // keeps nup <= len(grids) - 2, the top cell is never written, L:134)
             const bool two = c + 1 < nup;
-            const int c1 = two ? c + 1 : c;
-            const double t0 = cell_weight(c, rl, ru, psv, dz, rdz, g), t1 = cell_weight(c1, rl, ru, psv, dz, rdz, g);
-            sink.add2_fixed(c, mul(t0, w0), mul(t0, w1), two, c1, mul(t1, w0), mul(t1, w1));
+            const double ga = g[c], gb = g[c + 1], gc = g[c + 2];
+            const double t0 = mul(div_inv(fabs(sub(dmin(gb, ru), dmax(ga, rl))), dz, rdz), psv);
+            const double t1 = mul(div_inv(fabs(sub(dmin(gc, ru), dmax(gb, rl))), dz, rdz), psv);
+            sink.add2_fixed(c, mul(t0, w0), mul(t0, w1), two, c + 1, mul(t1, w0), mul(t1, w1));
         }
     } else {                                            // non-finite or outsized: fp64 atomics on the global deposit
         for (int c = nlow; c < nup; ++c) {
@@ -255,10 +260,12 @@ __device__ __forceinline__ void deposit_direct(bool ok, int nlow, int nup, doubl
         // Past it (stale bounds, a non-finite ray) contributions go to the global deposit in fp64.
         const double w0 = mul(v0, sink.scale), w1 = mul(v1, sink.scale1);
         const double f0 = mul(psv, fabs(w0)), f1 = mul(psv, fabs(w1));
-        bx += ok ? __double2float_ru(f0) : 0.f; by += ok ? __double2float_ru(f1) : 0.f;
-        const bool fits = mode == 1 ? (bx < sink.lim && by < sink.lim)
-                                    : (sink.scale < 0.0 || bx < sink.lim) && (sink.scale1 < 0.0 || by < sink.lim);
-        if (ok) deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, w0, w1, fits, dz, rdz, g, sink);
+        if (ok) {
+            bx += __double2float_ru(f0); by += __double2float_ru(f1);
+            const bool fits = mode == 1 ? (bx < sink.lim && by < sink.lim)
+                                        : (sink.scale < 0.0 || bx < sink.lim) && (sink.scale1 < 0.0 || by < sink.lim);
+            deposit_fixed(nlow, nup, rl, ru, psv, v0, v1, w0, w1, fits, dz, rdz, g, sink);
+        }
         return;
     }
     if (!ok) return;

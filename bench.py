@@ -57,9 +57,9 @@ NCU = {
     "c1": {"A": {"traffic_per_ray": 90.7, "fp64_frac": 0.350, "us_per_mray": 42.4},
            "B": {"traffic_per_ray": 107.6, "fp64_frac": 0.327, "us_per_mray": 32.7},
            "source": "profiles/r02am_const_dispersed_ncu_full_summary.json (3e6 rays, constant N, sheared, dispersed)"},
-    "c2": {"A": {"traffic_per_ray": 125.3, "fp64_frac": 0.398, "us_per_mray": 64.9},
-           "B": {"traffic_per_ray": 157.7, "fp64_frac": 0.420, "us_per_mray": 43.6},
-           "source": "profiles/r02bs_nz_bench_ncu_full_summary.json (the bench workload itself: 1.25e7 rays, dispersed)"},
+    "c2": {"A": {"traffic_per_ray": 125.1, "fp64_frac": 0.416, "us_per_mray": 62.7},
+           "B": {"traffic_per_ray": 157.8, "fp64_frac": 0.432, "us_per_mray": 42.2},
+           "source": "profiles/r02bw_nz_bench_ncu_full_summary.json (the bench workload itself: 1.25e7 rays, dispersed)"},
 }
 # one fp64 warp instruction per 2.1 cycles per SM sub-partition, 4 per SM, 148 SMs (profiles/r01_fp64_pipe_microbench.txt)
 FP64_PEAK_SOURCE = "measured DFMA issue rate, tools/micro/fp64_lat.cu (1 warp instruction / 2.1 cycles / SMSP) x 592 SMSPs x SM clock"
